@@ -1,0 +1,772 @@
+// api.cu -- plan lifecycle, the type 1/2/3 pipelines, the per-process plan cache and the C ABI.
+// Replaces lib/kernels.cc.cu (run_nufft), lib/cufinufft_wrapper.* and cuFINUFFT's
+// makeplan/setpts/execute/destroy (V/include/cufinufft/impl.h, V/src/cuda/{1,2,3}d/cufinufft*d.cu).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "plan.h"
+
+namespace b2n {
+
+// ------------------------------------------------------------------------------------ utilities
+struct StageTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t st;
+  bool on;
+  double *slot;
+  StageTimer(bool enable, cudaStream_t s, double *dst) : st(s), on(enable), slot(dst) {
+    if (on) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, st);
+    }
+  }
+  ~StageTimer() {
+    if (on) {
+      cudaEventRecord(b, st);
+      cudaEventSynchronize(b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      *slot += ms;
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
+    }
+  }
+};
+
+template <typename T> static size_t tile_bytes_for(int dim, int ns, const int *bin) {
+  return tile_smem_bytes<T>(dim, ns, bin);
+}
+
+static const int CAND2[][3] = {{32, 32, 1}, {32, 16, 1}, {16, 16, 1}, {16, 8, 1}, {8, 8, 1}, {8, 4, 1}, {4, 4, 1}, {2, 2, 1}};
+static const int CAND3[][3] = {{16, 16, 8}, {16, 8, 8}, {8, 8, 8}, {8, 8, 4}, {8, 4, 4}, {4, 4, 4}, {4, 4, 2}, {2, 2, 2}};
+constexpr size_t SMEM_3CTA = 76000, SMEM_2CTA = 115000, SMEM_1CTA = 232448;
+
+// B200 bin-size choice (replaces cufinufft_setup_binsize, V/src/cuda/common.cu:522-641): the
+// largest candidate whose tile + weight batch lets 3 CTAs share an SM's 227 KB; failing that 2,
+// then 1.  Returns false if no tile fits (caller falls back to the GM kernels).
+template <typename T> static bool choose_bins(int dim, int ns, int *bin) {
+  if (dim == 1) {
+    bin[0] = 1024; bin[1] = 1; bin[2] = 1;
+    return true;
+  }
+  const int(*cand)[3] = dim == 2 ? CAND2 : CAND3;
+  const size_t limits[3] = {SMEM_3CTA, SMEM_2CTA, SMEM_1CTA};
+  for (size_t lim : limits)
+    for (int i = 0; i < 8; i++) {
+      size_t b = tile_bytes_for<T>(dim, ns, cand[i]);
+      if (b > 0 && b <= lim) {
+        bin[0] = cand[i][0]; bin[1] = cand[i][1]; bin[2] = cand[i][2];
+        return true;
+      }
+    }
+  return false;
+}
+
+template <typename T> static void fill_table(HornerTable<T> &tab, int ns, double beta, bool direct, int *ncoef) {
+  double coef[MAX_NCOEF_H * 16];
+  int nc = horner_fit(ns, beta, sizeof(T) == 8, coef);
+  std::memset(&tab, 0, sizeof(tab));
+  for (int k = 0; k < nc; k++)
+    for (int j = 0; j < ns; j++) tab.c[k][j] = (T)coef[k * 16 + j];
+  tab.ncoef = nc;
+  tab.ns = ns;
+  tab.es_c = (T)(4.0 / ((double)ns * ns));
+  tab.es_beta = (T)beta;
+  tab.direct = direct ? 1 : 0;
+  *ncoef = nc;
+}
+
+// ------------------------------------------------------------------------------------ Plan
+template <typename T> Plan<T>::~Plan() {
+  cudaStream_t st = stream;
+  for (int d = 0; d < 3; d++) {
+    dev_free(fwker[d], st);
+    dev_free(pts.xs[d], st);
+    dev_free(xp[d], st);
+    dev_free(sp[d], st);
+  }
+  dev_free(fw, st);
+  dev_free(pts.idx, st);
+  dev_free(pts.bin_start, st);
+  dev_free(pts.sp_off, st);
+  dev_free(pts.sp_bin, st);
+  dev_free(prephase, st);
+  dev_free(deconv, st);
+  if (has_fft) cufftDestroy(fft);
+  delete inner;
+}
+
+template <typename T> void Plan<T>::set_stream(cudaStream_t s) {
+  stream = s;
+  if (has_fft) cufftSetStream(fft, s);
+  if (inner) inner->set_stream(s);
+}
+
+template <typename T>
+int Plan<T>::init(int type_, int dim_, const int64_t *n_modes, int iflag_, int ntransf_,
+                  double eps_, const b2n_opts *o) {
+  is_double = sizeof(T) == 8;
+  if (type_ < 1 || type_ > 3) {
+    fprintf(stderr, "[b200nufft] Invalid type (%d): should be 1, 2, or 3.\n", type_);
+    return B2N_ERR_TYPE_NOTVALID;
+  }
+  if (ntransf_ < 1) {
+    fprintf(stderr, "[b200nufft] Invalid ntransf (%d): should be at least 1.\n", ntransf_);
+    return B2N_ERR_NTRANS_NOTVALID;
+  }
+  type = type_;
+  dim = dim_;
+  iflag = iflag_ >= 0 ? 1 : -1;
+  ntransf = ntransf_;
+  eps = eps_;
+  if (o) opts = *o; else b2n_default_opts(&opts);
+  stream = (cudaStream_t)opts.gpu_stream;
+  if (opts.gpu_method < 0 || opts.gpu_method > 4) return B2N_ERR_METHOD_NOTVALID;
+  if (type == 3) opts.gpu_spreadinterponly = 1;  // outer plan only spreads (impl.h:115-117)
+  batch = opts.gpu_maxbatchsize > 0 ? opts.gpu_maxbatchsize : std::min(ntransf, 8);
+  batch = std::min(batch, ntransf);
+  if (opts.upsampfac == 0.0) {  // auto (impl.h:151-155)
+    opts.upsampfac = 2.0;
+    if (eps >= 1e-9 && type == 3) opts.upsampfac = 1.25;
+  }
+  sigma = opts.upsampfac;
+  int ier = setup_spreader(eps, sigma, opts.gpu_kerevalmeth, is_double, &ns, &beta);
+  if (ier > 1) return ier;
+  warn = ier;
+  fill_table<T>(tab, ns, beta, opts.gpu_kerevalmeth == 0, &ncoef);
+
+  // method: tile kernels wherever a tile fits, GM otherwise / on request / in 1-D
+  method = (opts.gpu_method == 1 || dim == 1) ? 1 : 2;
+  if (opts.gpu_binsizex > 0 || opts.gpu_binsizey > 0 || opts.gpu_binsizez > 0) {
+    bin[0] = std::max(opts.gpu_binsizex, 1);
+    bin[1] = dim > 1 ? std::max(opts.gpu_binsizey, 1) : 1;
+    bin[2] = dim > 2 ? std::max(opts.gpu_binsizez, 1) : 1;
+    if (method == 2) {
+      if (sizeof(T) == 4 && (bin[0] & 1)) return B2N_ERR_BINSIZE_NOTVALID;  // float tiles need even x bins
+      size_t b = tile_bytes_for<T>(dim, ns, bin);
+      if (b == 0 || b > SMEM_1CTA) {
+        if (opts.gpu_method == 0) method = 1;
+        else return B2N_ERR_INSUFFICIENT_SHMEM;
+      }
+    }
+  } else {
+    if (!choose_bins<T>(dim, ns, bin)) {
+      method = 1;
+      bin[0] = dim == 1 ? 1024 : 16; bin[1] = dim > 1 ? 16 : 1; bin[2] = dim > 2 ? 4 : 1;
+    }
+  }
+  maxsub = opts.gpu_maxsubprobsize > 0 ? opts.gpu_maxsubprobsize : 2048;
+
+  if (type != 3) {
+    nmodes = 1;
+    for (int d = 0; d < 3; d++) ms[d] = d < dim ? n_modes[d] : 1;
+    for (int d = 0; d < dim; d++) nmodes *= ms[d];
+    for (int d = 0; d < dim; d++)
+      nf[d] = opts.gpu_spreadinterponly ? ms[d] : set_nf_type12(ms[d], sigma, ns);
+    if (int e = alloc_grid()) return e;
+  }
+  if (opts.debug)
+    printf("[b200nufft] plan: type %d dim %d %s eps=%.3g sigma=%.3g ns=%d beta=%.4g ncoef=%d method=%s "
+           "bins=(%d,%d,%d) nf=(%ld,%ld,%ld) batch=%d\n",
+           type, dim, is_double ? "f64" : "f32", eps, sigma, ns, beta, ncoef, method == 2 ? "tile" : "GM",
+           bin[0], bin[1], bin[2], (long)nf[0], (long)nf[1], (long)nf[2], batch);
+  return warn;
+}
+
+// fine grid, kernel Fourier series and cuFFT plan for the current nf (types 1/2 at plan time,
+// type 3 outer/inner at setpts time)
+template <typename T> int Plan<T>::alloc_grid() {
+  nftot = 1;
+  for (int d = 0; d < 3; d++) {
+    if (d >= dim) nf[d] = 1;
+    nftot *= nf[d];
+    nbin[d] = d < dim ? cdiv(nf[d], bin[d]) : 1;
+  }
+  nbins = (int64_t)nbin[0] * nbin[1] * nbin[2];
+  for (int d = 0; d < dim; d++)
+    if (nf[d] > 0x7fffffffLL) return B2N_ERR_NDATA_NOTVALID;
+  if (nbins > 0x7fffffffLL) return B2N_ERR_NDATA_NOTVALID;
+  if (opts.gpu_spreadinterponly) return 0;  // grid is the caller's array; no FFT, no kernel FT
+  const int64_t need = (int64_t)batch * nftot;
+  if (need > cap_fw) {
+    dev_free(fw, stream);
+    fw = nullptr;
+    cap_fw = 0;
+    if (int e = dev_alloc_t(&fw, (size_t)need, stream)) return e;
+    cap_fw = need;
+  }
+  for (int d = 0; d < dim; d++) {
+    dev_free(fwker[d], stream);
+    fwker[d] = nullptr;
+    if (int e = dev_alloc_t(&fwker[d], (size_t)(nf[d] / 2 + 1), stream)) return e;
+  }
+  if (has_fft) { cufftDestroy(fft); has_fft = false; }
+  long long n[3];
+  for (int d = 0; d < dim; d++) n[d] = nf[dim - 1 - d];  // slowest first
+  if (cufftCreate(&fft) != CUFFT_SUCCESS) return B2N_ERR_CUDA_FAILURE;
+  size_t work = 0;
+  cufftResult r = cufftMakePlanMany64(fft, dim, n, nullptr, 1, nftot, nullptr, 1, nftot,
+                                      sizeof(T) == 4 ? CUFFT_C2C : CUFFT_Z2Z, batch, &work);
+  if (r != CUFFT_SUCCESS) {
+    fprintf(stderr, "[b200nufft] cufft plan failed (%d)\n", (int)r);
+    cufftDestroy(fft);
+    return B2N_ERR_CUDA_FAILURE;
+  }
+  has_fft = true;
+  cufftSetStream(fft, stream);
+  return compute_fseries<T>(*this);
+}
+
+template <typename T>
+int Plan<T>::setpts(int64_t M, const void *x, const void *y, const void *z, int64_t N, const void *s,
+                    const void *t, const void *u) {
+  if (M < 0 || M > 0x7fffffffLL) return B2N_ERR_NDATA_NOTVALID;
+  if (type != 3) return setpts12(M, (const T *)x, (const T *)y, (const T *)z);
+  return setpts3(M, (const T *)x, (const T *)y, (const T *)z, N, (const T *)s, (const T *)t, (const T *)u);
+}
+
+template <typename T> int Plan<T>::setpts12(int64_t M, const T *x, const T *y, const T *z) {
+  StageTimer tm(opts.debug != 0, stream, &timings[0]);
+  return binsort_points<T>(*this, M, x, y, z);
+}
+
+// Type-3 setpts: V/include/cufinufft/impl.h:461-823
+template <typename T>
+int Plan<T>::setpts3(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s, const T *t,
+                     const T *u) {
+  if (N < 0) return B2N_ERR_NUM_NU_PTS_INVALID;
+  if (N > 0x7fffffffLL) return B2N_ERR_NUM_NU_PTS_INVALID;
+  const T *X[3] = {x, y, z}, *S[3] = {s, t, u};
+  for (int d = 0; d < dim; d++)
+    if (S[d] == nullptr) return B2N_ERR_INVALID_ARGUMENT;
+  N3 = N;
+  double lohi[12];
+  {
+    StageTimer tm(opts.debug != 0, stream, &timings[5]);
+    if (int e = t3_minmax<T>(stream, dim, M, X, N, S, lohi)) return e;
+  }
+  for (int d = 0; d < dim; d++) {
+    widcen(lohi[2 * d], lohi[2 * d + 1], is_double, &t3X[d], &t3C[d]);
+    widcen(lohi[6 + 2 * d], lohi[6 + 2 * d + 1], is_double, &t3S[d], &t3D[d]);
+    set_nhg_type3(t3S[d], t3X[d], sigma, ns, is_double, &nf[d], &t3h[d], &t3gam[d]);
+  }
+  if (opts.debug)
+    for (int d = 0; d < dim; d++)
+      printf("[b200nufft] t3 dim %d: X=%.3g C=%.3g S=%.3g D=%.3g gam=%g nf=%ld h=%.3g\n", d, t3X[d],
+             t3C[d], t3S[d], t3D[d], t3gam[d], (long)nf[d], t3h[d]);
+  // outer grid: spread-only plan geometry + its own fine grid (batch * nf)
+  nftot = 1;
+  for (int d = 0; d < 3; d++) {
+    if (d >= dim) nf[d] = 1;
+    nftot *= nf[d];
+    nbin[d] = d < dim ? cdiv(nf[d], bin[d]) : 1;
+  }
+  nbins = (int64_t)nbin[0] * nbin[1] * nbin[2];
+  const int64_t need = (int64_t)batch * nftot;
+  if (need > cap_fw) {
+    dev_free(fw, stream);
+    fw = nullptr;
+    cap_fw = 0;
+    if (int e = dev_alloc_t(&fw, (size_t)need, stream)) return e;
+    cap_fw = need;
+  }
+  if (M > cap_xp) {
+    for (int d = 0; d < dim; d++) {
+      dev_free(xp[d], stream);
+      xp[d] = nullptr;
+      if (int e = dev_alloc_t(&xp[d], (size_t)M, stream)) return e;
+    }
+    dev_free(prephase, stream);
+    prephase = nullptr;
+    if (int e = dev_alloc_t(&prephase, (size_t)M, stream)) return e;
+    cap_xp = M;
+  }
+  if (N > cap_sp3) {
+    for (int d = 0; d < dim; d++) {
+      dev_free(sp[d], stream);
+      sp[d] = nullptr;
+      if (int e = dev_alloc_t(&sp[d], (size_t)N, stream)) return e;
+    }
+    dev_free(deconv, stream);
+    deconv = nullptr;
+    if (int e = dev_alloc_t(&deconv, (size_t)N, stream)) return e;
+    cap_sp3 = N;
+  }
+  pts.M = M;
+  {
+    StageTimer tm(opts.debug != 0, stream, &timings[5]);
+    if (int e = t3_prepare<T>(*this, X, S)) return e;
+  }
+  // bin-sort the rescaled sources for the outer spread
+  if (int e = setpts12(M, xp[0], xp[1], xp[2])) return e;
+  // inner type-2 plan: modes = outer fine grid, modeord 0, same iflag/eps/sigma (impl.h:795-812)
+  b2n_opts io = opts;
+  io.gpu_spreadinterponly = 0;
+  io.gpu_method = 0;
+  io.modeord = 0;
+  io.gpu_maxbatchsize = batch;
+  io.gpu_stream = stream;
+  bool rebuild = inner == nullptr;
+  if (inner)
+    for (int d = 0; d < dim; d++)
+      if (inner->ms[d] != nf[d]) rebuild = true;
+  if (rebuild) {
+    delete inner;
+    inner = new (std::nothrow) Plan<T>();
+    if (!inner) return B2N_ERR_ALLOC;
+    int e = inner->init(2, dim, nf, iflag, batch, eps, &io);
+    if (e > 1) {
+      delete inner;
+      inner = nullptr;
+      return e;
+    }
+  }
+  return inner->setpts12(N, sp[0], sp[1], sp[2]);
+}
+
+template <typename T> int Plan<T>::execute(void *c, void *fk) {
+  if (type == 1) return exec1((cpx<T> *)c, (cpx<T> *)fk);
+  if (type == 2) return exec2((cpx<T> *)c, (cpx<T> *)fk, nullptr);
+  return exec3((cpx<T> *)c, (cpx<T> *)fk);
+}
+
+template <typename T> static int run_fft(Plan<T> &p) {
+  const int dir = p.iflag >= 0 ? CUFFT_INVERSE : CUFFT_FORWARD;  // cufft_ex(.., iflag): types.h:108-115
+  cufftResult r;
+  if (sizeof(T) == 4) r = cufftExecC2C(p.fft, (cufftComplex *)p.fw, (cufftComplex *)p.fw, dir);
+  else r = cufftExecZ2Z(p.fft, (cufftDoubleComplex *)p.fw, (cufftDoubleComplex *)p.fw, dir);
+  return r == CUFFT_SUCCESS ? 0 : B2N_ERR_CUDA_FAILURE;
+}
+
+// Type 1: V/src/cuda/3d/cufinufft3d.cu:18-73 (and 1d/2d twins)
+template <typename T> int Plan<T>::exec1(cpx<T> *c, cpx<T> *fk) {
+  const bool dbg = opts.debug != 0;
+  const int64_t M = pts.M;
+  for (int i = 0; i * batch < ntransf; i++) {
+    const int blk = std::min(ntransf - i * batch, batch);
+    cpx<T> *cs = c + (int64_t)i * batch * M;
+    cpx<T> *fks = fk + (int64_t)i * batch * nmodes;
+    cpx<T> *grid = opts.gpu_spreadinterponly ? fks : fw;
+    {
+      StageTimer tm(dbg, stream, &timings[6]);
+      B2N_CUDA_OK(cudaMemsetAsync(grid, 0, sizeof(cpx<T>) * (size_t)blk * nftot, stream));
+    }
+    {
+      StageTimer tm(dbg, stream, &timings[1]);
+      int e = method == 2 ? spread_tile<T>(*this, cs, nullptr, grid, blk)
+                          : spread_gm<T>(*this, cs, nullptr, grid, blk);
+      if (e) return e;
+    }
+    if (opts.gpu_spreadinterponly) continue;
+    {
+      StageTimer tm(dbg, stream, &timings[2]);
+      if (int e = run_fft(*this)) return e;
+    }
+    {
+      StageTimer tm(dbg, stream, &timings[3]);
+      if (int e = deconvolve<T>(*this, fw, fks, blk)) return e;
+    }
+  }
+  return 0;
+}
+
+// Type 2: V/src/cuda/3d/cufinufft3d.cu:75-125
+template <typename T> int Plan<T>::exec2(cpx<T> *c, cpx<T> *fk, const cpx<T> *postscale) {
+  const bool dbg = opts.debug != 0;
+  const int64_t M = pts.M;
+  for (int i = 0; i * batch < ntransf; i++) {
+    const int blk = std::min(ntransf - i * batch, batch);
+    cpx<T> *cs = c + (int64_t)i * batch * M;
+    cpx<T> *fks = fk + (int64_t)i * batch * nmodes;
+    const cpx<T> *grid = fks;
+    if (!opts.gpu_spreadinterponly) {
+      {
+        StageTimer tm(dbg, stream, &timings[3]);
+        if (int e = amplify<T>(*this, fw, fks, blk)) return e;
+      }
+      {
+        StageTimer tm(dbg, stream, &timings[2]);
+        if (int e = run_fft(*this)) return e;
+      }
+      grid = fw;
+    }
+    {
+      StageTimer tm(dbg, stream, &timings[4]);
+      int e = method == 2 ? interp_tile<T>(*this, cs, postscale, grid, blk)
+                          : interp_gm<T>(*this, cs, postscale, grid, blk);
+      if (e) return e;
+    }
+  }
+  return 0;
+}
+
+// Type 3: V/src/cuda/3d/cufinufft3d.cu:127-183.  The reference makes two extra passes per
+// transform (prephase*c into CpBatch; deconv*f in place); here the prephase multiply is fused
+// into the spreader's strength load and the deconv multiply into the interpolator's store.
+template <typename T> int Plan<T>::exec3(cpx<T> *c, cpx<T> *fk) {
+  const bool dbg = opts.debug != 0;
+  const int64_t M = pts.M;
+  bool anyD = false;
+  for (int d = 0; d < dim; d++) anyD = anyD || t3D[d] != 0;
+  for (int i = 0; i * batch < ntransf; i++) {
+    const int blk = std::min(ntransf - i * batch, batch);
+    cpx<T> *cs = c + (int64_t)i * batch * M;
+    cpx<T> *fks = fk + (int64_t)i * batch * N3;
+    {
+      StageTimer tm(dbg, stream, &timings[6]);
+      B2N_CUDA_OK(cudaMemsetAsync(fw, 0, sizeof(cpx<T>) * (size_t)blk * nftot, stream));
+    }
+    {
+      StageTimer tm(dbg, stream, &timings[1]);
+      int e = method == 2 ? spread_tile<T>(*this, cs, anyD ? prephase : nullptr, fw, blk)
+                          : spread_gm<T>(*this, cs, anyD ? prephase : nullptr, fw, blk);
+      if (e) return e;
+    }
+    inner->ntransf = blk;
+    if (int e = inner->exec2(fks, fw, deconv)) return e;
+    if (dbg)
+      for (int k = 2; k <= 4; k++) { timings[k] += inner->timings[k]; inner->timings[k] = 0; }
+  }
+  return 0;
+}
+
+template <typename T> void Plan<T>::info(b2n_plan_info *o) {
+  std::memset(o, 0, sizeof(*o));
+  o->type = type; o->dim = dim; o->is_double = is_double; o->ns = ns; o->method = method;
+  o->ntransf = ntransf; o->batchsize = batch; o->ncoef = ncoef; o->beta = beta; o->upsampfac = sigma;
+  for (int d = 0; d < 3; d++) {
+    o->nf[d] = nf[d]; o->ms[d] = ms[d]; o->binsize[d] = bin[d]; o->nbins[d] = nbin[d];
+    o->t3_X[d] = t3X[d]; o->t3_C[d] = t3C[d]; o->t3_S[d] = t3S[d]; o->t3_D[d] = t3D[d];
+    o->t3_h[d] = t3h[d]; o->t3_gam[d] = t3gam[d];
+    o->t3_nf_inner[d] = inner ? inner->nf[d] : 0;
+  }
+  o->M = pts.M;
+  o->N = N3;
+}
+
+template <typename T>
+int Plan<T>::sort_get(const int32_t **idx, const int32_t **bin_start, int64_t *nb) {
+  *idx = pts.idx;
+  *bin_start = pts.bin_start;
+  *nb = nbins;
+  return pts.idx ? 0 : B2N_ERR_PLAN_NOTVALID;
+}
+
+template struct Plan<float>;
+template struct Plan<double>;
+
+// ------------------------------------------------------------------------------------ plan cache
+// run_nufft in the reference builds and destroys a plan (cuFFT plan, ~12 allocations, kernel FT)
+// on EVERY custom call (lib/kernels.cc.cu:49-51,84).  Here finished plans are parked, keyed by
+// everything that shapes them, and re-used by the next identical call; an event orders re-use
+// across streams.  Thread-safe: a plan is owned by exactly one caller while checked out.
+struct CacheKey {
+  int type, dim, is_double, iflag, ntransf, device;
+  int64_t nk[3];
+  double eps, upsampfac;
+  int modeord, method, sort, kerevalmeth, maxbatch, debug;
+  bool operator==(const CacheKey &o) const { return std::memcmp(this, &o, sizeof(CacheKey)) == 0; }
+};
+struct CacheEntry {
+  CacheKey key;
+  PlanBase *plan;
+  cudaEvent_t done;
+};
+static std::mutex g_mu;
+static std::vector<CacheEntry> g_cache;
+constexpr size_t CACHE_MAX = 8;
+
+static PlanBase *cache_take(const CacheKey &k, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (size_t i = 0; i < g_cache.size(); i++)
+    if (g_cache[i].key == k) {
+      CacheEntry e = g_cache[i];
+      g_cache.erase(g_cache.begin() + i);
+      cudaStreamWaitEvent(st, e.done, 0);
+      cudaEventDestroy(e.done);
+      return e.plan;
+    }
+  return nullptr;
+}
+static void cache_put(const CacheKey &k, PlanBase *p, cudaStream_t st) {
+  CacheEntry e;
+  e.key = k;
+  e.plan = p;
+  cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming);
+  cudaEventRecord(e.done, st);
+  PlanBase *evict = nullptr;
+  cudaEvent_t evict_ev = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_cache.size() >= CACHE_MAX) {
+      evict = g_cache.front().plan;
+      evict_ev = g_cache.front().done;
+      g_cache.erase(g_cache.begin());
+    }
+    g_cache.push_back(e);
+  }
+  if (evict) {
+    cudaEventSynchronize(evict_ev);
+    cudaEventDestroy(evict_ev);
+    delete evict;
+  }
+}
+
+}  // namespace b2n
+
+// =========================================================================================== C ABI
+using namespace b2n;
+
+extern "C" {
+
+const char *b2n_version(void) { return "b200nufft 0.1 (sm_100a)"; }
+
+void b2n_default_opts(b2n_opts *o) {  // defaults of V/src/cuda/cufinufft.cu:133-152
+  std::memset(o, 0, sizeof(*o));
+  o->modeord = 0;
+  o->upsampfac = 0.0;
+  o->gpu_method = 0;
+  o->gpu_sort = 1;
+  o->gpu_kerevalmeth = 1;
+  o->gpu_maxbatchsize = 0;
+  o->debug = 0;
+  o->gpu_maxsubprobsize = 0;
+  o->gpu_spreadinterponly = 0;
+  o->gpu_device_id = 0;
+  o->gpu_stream = nullptr;
+}
+
+static bool invalid_modes(int type, int dim, const int64_t *m) {  // cufinufft.cu:12-29
+  if (type == 3) return false;
+  int64_t tot = 1;
+  for (int i = 0; i < dim; i++) {
+    if (m[i] > 0x7fffffffLL || m[i] <= 0) return true;
+    tot *= m[i];
+    if (tot > 0x7fffffffLL) return true;
+  }
+  return false;
+}
+
+int b2n_makeplan(int type, int dim, const int64_t *n_modes, int iflag, int ntransf, double eps,
+                 int is_double, b2n_plan *plan, const b2n_opts *opts) {
+  *plan = nullptr;
+  if (dim < 1 || dim > 3) {
+    fprintf(stderr, "[b200nufft] Invalid dim (%d), should be 1, 2 or 3.\n", dim);
+    return B2N_ERR_DIM_NOTVALID;
+  }
+  if (type != 3 && (!n_modes || invalid_modes(type, dim, n_modes))) return B2N_ERR_NDATA_NOTVALID;
+  PlanBase *p = nullptr;
+  int ier;
+  try {
+    if (is_double) {
+      auto *q = new Plan<double>();
+      p = q;
+      ier = q->init(type, dim, n_modes, iflag, ntransf, eps, opts);
+    } else {
+      auto *q = new Plan<float>();
+      p = q;
+      ier = q->init(type, dim, n_modes, iflag, ntransf, eps, opts);
+    }
+  } catch (...) {
+    delete p;
+    return B2N_ERR_ALLOC;
+  }
+  if (ier > 1) {
+    delete p;
+    return ier;
+  }
+  *plan = reinterpret_cast<b2n_plan>(p);
+  return ier;
+}
+
+int b2n_setpts(b2n_plan plan, int64_t M, const void *x, const void *y, const void *z, int64_t N,
+               const void *s, const void *t, const void *u) {
+  if (!plan) return B2N_ERR_PLAN_NOTVALID;
+  try {
+    return reinterpret_cast<PlanBase *>(plan)->setpts(M, x, y, z, N, s, t, u);
+  } catch (...) {
+    return B2N_ERR_ALLOC;
+  }
+}
+
+int b2n_execute(b2n_plan plan, void *c, void *fk) {
+  if (!plan) return B2N_ERR_PLAN_NOTVALID;
+  try {
+    return reinterpret_cast<PlanBase *>(plan)->execute(c, fk);
+  } catch (...) {
+    return B2N_ERR_CUDA_FAILURE;
+  }
+}
+
+int b2n_destroy(b2n_plan plan) {
+  if (!plan) return B2N_ERR_PLAN_NOTVALID;  // cufinufft_destroy(NULL) -> 16
+  delete reinterpret_cast<PlanBase *>(plan);
+  return 0;
+}
+
+int b2n_plan_info_get(b2n_plan plan, b2n_plan_info *info) {
+  if (!plan) return B2N_ERR_PLAN_NOTVALID;
+  reinterpret_cast<PlanBase *>(plan)->info(info);
+  return 0;
+}
+
+int b2n_plan_sort_get(b2n_plan plan, const int32_t **idx, const int32_t **bin_start, int64_t *nbins) {
+  if (!plan) return B2N_ERR_PLAN_NOTVALID;
+  return reinterpret_cast<PlanBase *>(plan)->sort_get(idx, bin_start, nbins);
+}
+
+int b2n_plan_timings(b2n_plan plan, double *ms7) {
+  if (!plan) return B2N_ERR_PLAN_NOTVALID;
+  PlanBase *p = reinterpret_cast<PlanBase *>(plan);
+  for (int i = 0; i < 7; i++) { ms7[i] = p->timings[i]; p->timings[i] = 0; }
+  return 0;
+}
+
+void b2n_cache_clear(void) {
+  std::vector<CacheEntry> old;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    old.swap(g_cache);
+  }
+  for (auto &e : old) {
+    cudaEventSynchronize(e.done);
+    cudaEventDestroy(e.done);
+    delete e.plan;
+  }
+}
+
+int b2n_run(int type, int dim, int is_double, void *stream_, double eps, int iflag, int64_t n_tot,
+            int n_transf, int64_t n_j, const int64_t *n_k, const b2n_opts *opts_in, const void *src,
+            const void *const *pts, const void *const *tgt, void *out) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  b2n_opts o;
+  if (opts_in) o = *opts_in; else b2n_default_opts(&o);
+  o.gpu_stream = stream;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B2N_ERR_CUDA_FAILURE;  // kernels.cc.cu:40-47
+  o.gpu_device_id = dev;
+  if (dim < 1 || dim > 3) return B2N_ERR_DIM_NOTVALID;
+  if (type < 1 || type > 3) return B2N_ERR_TYPE_NOTVALID;
+
+  CacheKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.type = type; key.dim = dim; key.is_double = is_double; key.iflag = iflag >= 0 ? 1 : -1;
+  key.ntransf = n_transf; key.device = dev;
+  for (int d = 0; d < 3; d++) key.nk[d] = (type != 3 && d < dim) ? n_k[d] : 0;
+  key.eps = eps; key.upsampfac = o.upsampfac; key.modeord = o.modeord; key.method = o.gpu_method;
+  key.sort = o.gpu_sort; key.kerevalmeth = o.gpu_kerevalmeth; key.maxbatch = o.gpu_maxbatchsize;
+  key.debug = o.debug;
+
+  PlanBase *p = cache_take(key, stream);
+  int warn = 0;
+  if (p) {
+    p->set_stream(stream);
+  } else {
+    b2n_plan h = nullptr;
+    int64_t nk3[3] = {n_k ? n_k[0] : 1, n_k ? n_k[1] : 1, n_k ? n_k[2] : 1};
+    int ier = b2n_makeplan(type, dim, nk3, iflag, n_transf, eps, is_double, &h, &o);
+    if (ier > 1) return ier;  // ret == 1 is a warning (kernels.cc.cu:52)
+    warn = ier;
+    p = reinterpret_cast<PlanBase *>(h);
+  }
+  int64_t n_k_total = 1;
+  if (type != 3) for (int d = 0; d < dim; d++) n_k_total *= n_k[d];
+  else n_k_total = n_k[0];
+  const size_t rs = is_double ? 8 : 4, cs = 2 * rs;
+  const int64_t n_src = type == 2 ? n_k_total : n_j;   // per-transform source length
+  const int64_t n_out = type == 2 ? n_j : n_k_total;   // per-transform output length
+  for (int64_t index = 0; index < n_tot; index++) {
+    const void *P[3] = {nullptr, nullptr, nullptr}, *Tg[3] = {nullptr, nullptr, nullptr};
+    for (int d = 0; d < dim; d++) {
+      P[d] = (const char *)pts[d] + (size_t)index * n_j * rs;
+      if (type == 3) Tg[d] = (const char *)tgt[d] + (size_t)index * n_k_total * rs;
+    }
+    int ret = p->setpts(n_j, P[0], P[1], P[2], type == 3 ? n_k_total : 0, Tg[0], Tg[1], Tg[2]);
+    if (ret != 0) {
+      cudaStreamSynchronize(stream);
+      delete p;
+      return ret;
+    }
+    const char *s_i = (const char *)src + (size_t)index * n_src * n_transf * cs;
+    char *o_i = (char *)out + (size_t)index * n_out * n_transf * cs;
+    // execute(c, fk): c = nonuniform side, fk = uniform side (or type-3 targets)
+    if (type == 2) ret = p->execute((void *)o_i, (void *)s_i);
+    else ret = p->execute((void *)s_i, (void *)o_i);
+    if (ret != 0) {
+      cudaStreamSynchronize(stream);
+      delete p;
+      return ret;
+    }
+  }
+  if (o.debug) cudaStreamSynchronize(stream);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    fprintf(stderr, "[b200nufft] CUDA error: %s\n", cudaGetErrorString(ce));
+    cudaStreamSynchronize(stream);
+    delete p;
+    return B2N_ERR_CUDA_FAILURE;
+  }
+  cache_put(key, p, stream);
+  return warn;
+}
+
+int b2n_run_host(int type, int dim, int is_double, double eps, int iflag, int64_t n_tot, int n_transf,
+                 int64_t n_j, const int64_t *n_k, const b2n_opts *opts, const void *src,
+                 const void *const *pts, const void *const *tgt, void *out) {
+  if (dim < 1 || dim > 3) return B2N_ERR_DIM_NOTVALID;
+  if (type < 1 || type > 3) return B2N_ERR_TYPE_NOTVALID;
+  cudaStream_t st = opts && opts->gpu_stream ? (cudaStream_t)opts->gpu_stream : 0;
+  int64_t n_k_total = 1;
+  if (type != 3) for (int d = 0; d < dim; d++) n_k_total *= n_k[d];
+  else n_k_total = n_k[0];
+  const size_t rs = is_double ? 8 : 4, cs = 2 * rs;
+  const size_t src_b = (size_t)n_tot * n_transf * (type == 2 ? n_k_total : n_j) * cs;
+  const size_t out_b = (size_t)n_tot * n_transf * (type == 2 ? n_j : n_k_total) * cs;
+  const size_t pt_b = (size_t)n_tot * n_j * rs, tg_b = (size_t)n_tot * n_k_total * rs;
+  void *d_src = nullptr, *d_out = nullptr, *d_p[3] = {nullptr, nullptr, nullptr}, *d_t[3] = {nullptr, nullptr, nullptr};
+  int rc = 0;
+  auto cleanup = [&]() {
+    dev_free(d_src, st);
+    dev_free(d_out, st);
+    for (int d = 0; d < 3; d++) { dev_free(d_p[d], st); dev_free(d_t[d], st); }
+  };
+  if ((rc = dev_alloc(&d_src, src_b, st)) || (rc = dev_alloc(&d_out, out_b, st))) { cleanup(); return rc; }
+  for (int d = 0; d < dim; d++) {
+    if ((rc = dev_alloc(&d_p[d], pt_b, st))) { cleanup(); return rc; }
+    if (type == 3 && (rc = dev_alloc(&d_t[d], tg_b, st))) { cleanup(); return rc; }
+  }
+  cudaMemcpyAsync(d_src, src, src_b, cudaMemcpyHostToDevice, st);
+  for (int d = 0; d < dim; d++) {
+    cudaMemcpyAsync(d_p[d], pts[d], pt_b, cudaMemcpyHostToDevice, st);
+    if (type == 3) cudaMemcpyAsync(d_t[d], tgt[d], tg_b, cudaMemcpyHostToDevice, st);
+  }
+  rc = b2n_run(type, dim, is_double, st, eps, iflag, n_tot, n_transf, n_j, n_k, opts, d_src, d_p,
+               type == 3 ? d_t : nullptr, d_out);
+  if (rc <= 1) {
+    cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = B2N_ERR_CUDA_FAILURE;
+  }
+  cleanup();
+  return rc;
+}
+
+int b2n_setup_spreader(double eps, double upsampfac, int kerevalmeth, int is_double, int *ns, double *beta) {
+  return setup_spreader(eps, upsampfac, kerevalmeth, is_double != 0, ns, beta);
+}
+int64_t b2n_next235beven(int64_t n, int64_t b) { return next235beven(n, b); }
+int64_t b2n_set_nf_type12(int64_t ms, double upsampfac, int ns) { return set_nf_type12(ms, upsampfac, ns); }
+void b2n_fseries(int64_t nf, int ns, double beta, double *out) { fseries_host(nf, ns, beta, out); }
+int b2n_horner_table(int ns, double beta, int is_double, double *coef) {
+  return horner_fit(ns, beta, is_double != 0, coef);
+}
+void b2n_default_binsize(int dim, int ns, int is_double, int type, int *bin) {
+  (void)type;
+  bool ok = is_double ? choose_bins<double>(dim, ns, bin) : choose_bins<float>(dim, ns, bin);
+  if (!ok) { bin[0] = bin[1] = bin[2] = 0; }
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// plan.h -- plan state + internal stage entry points of libb200nufft.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "hostmath.h"
+
+namespace b2n {
+
+struct StageTimer;
+
+// Geometry of one bin-sorted point set (the state cuFINUFFT keeps in idxnupts / binsize /
+// binstartpts / subprob_to_bin -- V/include/cufinufft/types.h:30-101), plus the folded
+// coordinates stored in sorted order so spread/interp read them coalesced.
+template <typename T> struct PointSet {
+  int64_t M = 0;
+  T *xs[3] = {nullptr, nullptr, nullptr};  // fold_rescale'd coords, sorted by bin   [M]
+  int32_t *idx = nullptr;                  // sorted position -> original index      [M]
+  int32_t *bin_start = nullptr;            // exclusive scan of bin histogram        [nbins+1]
+  int32_t *sp_off = nullptr;               // exclusive scan of subproblems per bin  [nbins+1]
+  int32_t *sp_bin = nullptr;               // subproblem -> bin                      [sp_cap]
+  int64_t sp_cap = 0;                      // host-known upper bound on #subproblems
+  int64_t cap_M = 0, cap_bins = 0, cap_sp = 0;
+};
+
+struct PlanBase {
+  virtual ~PlanBase() {}
+  virtual int setpts(int64_t M, const void *x, const void *y, const void *z, int64_t N,
+                     const void *s, const void *t, const void *u) = 0;
+  virtual int execute(void *c, void *fk) = 0;
+  virtual void info(b2n_plan_info *out) = 0;
+  virtual int sort_get(const int32_t **idx, const int32_t **bin_start, int64_t *nbins) = 0;
+  virtual void set_stream(cudaStream_t s) = 0;
+  bool is_double = false;
+  double timings[7] = {0, 0, 0, 0, 0, 0, 0};
+};
+
+template <typename T> struct Plan : PlanBase {
+  int type = 0, dim = 0, iflag = 1, ntransf = 1, batch = 1;
+  double eps = 0;
+  b2n_opts opts;
+  int method = 0;  // 1 = GM kernels, 2 = tile kernels
+  int ns = 0, ncoef = 0;
+  double beta = 0, sigma = 2.0;
+  int warn = 0;
+  int64_t ms[3] = {1, 1, 1};
+  int64_t nmodes = 1;
+  int64_t nf[3] = {1, 1, 1};
+  int64_t nftot = 1;
+  int bin[3] = {1, 1, 1};
+  int nbin[3] = {1, 1, 1};
+  int64_t nbins = 1;
+  int maxsub = 1024;
+  HornerTable<T> tab;
+  cudaStream_t stream = 0;
+
+  T *fwker[3] = {nullptr, nullptr, nullptr};  // kernel Fourier series, nf_d/2+1 each
+  cpx<T> *fw = nullptr;                       // fine grid(s): batch * nftot
+  cufftHandle fft = 0;
+  bool has_fft = false;
+
+  PointSet<T> pts;
+
+  // ---- type 3 (V/include/cufinufft/types.h:84-100 type3_params + prephase/deconv) ----
+  int64_t N3 = 0;
+  double t3X[3] = {0, 0, 0}, t3C[3] = {0, 0, 0}, t3S[3] = {0, 0, 0}, t3D[3] = {0, 0, 0};
+  double t3h[3] = {1, 1, 1}, t3gam[3] = {1, 1, 1};
+  T *xp[3] = {nullptr, nullptr, nullptr};  // rescaled sources x' [M]
+  T *sp[3] = {nullptr, nullptr, nullptr};  // rescaled targets s' [N]
+  cpx<T> *prephase = nullptr;              // [M]
+  cpx<T> *deconv = nullptr;                // [N]
+  Plan<T> *inner = nullptr;                // inner type-2 plan (impl.h:795-812)
+  int64_t cap_xp = 0, cap_sp3 = 0, cap_fw = 0;
+
+  ~Plan() override;
+  int init(int type, int dim, const int64_t *n_modes, int iflag, int ntransf, double eps,
+           const b2n_opts *opts);
+  int alloc_grid();
+  int setpts(int64_t M, const void *x, const void *y, const void *z, int64_t N, const void *s,
+             const void *t, const void *u) override;
+  int setpts12(int64_t M, const T *x, const T *y, const T *z);
+  int setpts3(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s, const T *t,
+              const T *u);
+  int execute(void *c, void *fk) override;
+  int exec1(cpx<T> *c, cpx<T> *fk);
+  int exec2(cpx<T> *c, cpx<T> *fk, const cpx<T> *postscale);
+  int exec3(cpx<T> *c, cpx<T> *fk);
+  void info(b2n_plan_info *out) override;
+  int sort_get(const int32_t **idx, const int32_t **bin_start, int64_t *nbins) override;
+  void set_stream(cudaStream_t s) override;
+};
+
+// ---- stage launchers (one per .cu file) -------------------------------------------------------
+template <typename T>
+int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z);
+
+// strengths c (gathered through pts.idx, optionally multiplied by prescale[idx]) -> fw (+=)
+template <typename T>
+int spread_tile(Plan<T> &p, const cpx<T> *c, const cpx<T> *prescale, cpx<T> *fw, int ntr);
+template <typename T>
+int spread_gm(Plan<T> &p, const cpx<T> *c, const cpx<T> *prescale, cpx<T> *fw, int ntr);
+// fw -> c[idx] (optionally multiplied by postscale[idx])
+template <typename T>
+int interp_tile(Plan<T> &p, cpx<T> *c, const cpx<T> *postscale, const cpx<T> *fw, int ntr);
+template <typename T>
+int interp_gm(Plan<T> &p, cpx<T> *c, const cpx<T> *postscale, const cpx<T> *fw, int ntr);
+
+// smem bytes the tile kernels need for (dim, ns, bins); 0 if the combination is unsupported
+template <typename T> size_t tile_smem_bytes(int dim, int ns, const int *bin);
+
+template <typename T>
+int deconvolve(Plan<T> &p, const cpx<T> *fw, cpx<T> *fk, int ntr);   // type 1 step 3
+template <typename T>
+int amplify(Plan<T> &p, cpx<T> *fw, const cpx<T> *fk, int ntr);      // type 2 step 1 (+zero pad)
+template <typename T> int compute_fseries(Plan<T> &p);
+
+template <typename T>
+int t3_minmax(cudaStream_t st, int dim, int64_t M, const T *const *x, int64_t N,
+              const T *const *s, double *lohi /* [12]: per dim lo,hi of x then of s */);
+template <typename T> int t3_prepare(Plan<T> &p, const T *const *x, const T *const *s);
+
+int dev_alloc(void **p, size_t bytes, cudaStream_t st);
+void dev_free(void *p, cudaStream_t st);
+template <typename U> inline int dev_alloc_t(U **p, size_t count, cudaStream_t st) {
+  return dev_alloc((void **)p, count * sizeof(U), st);
+}
+int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t st);
+
+}  // namespace b2n
