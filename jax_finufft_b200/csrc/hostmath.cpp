@@ -249,18 +249,23 @@ static double fit_interval(int ns, double beta, int j, int nc, double *coef_hi_f
 }
 
 int horner_fit(int ns, double beta, bool is_double, double *coef /* [MAX_NCOEF_H][16] */) {
-  // target: well inside the kernel's own aliasing error 10^(1-ns), and no tighter than the
-  // arithmetic it will be evaluated in
-  double tol = 0.02 * std::pow(10.0, 1 - ns);
-  double floor_tol = is_double ? 2e-15 : 1.5e-8;
-  tol = std::max(tol, floor_tol);
+  // The ES kernel has a square-root endpoint singularity at |x| = ns/2, so the fit error of the
+  // two outermost intervals saturates (at ~0.15 * 10^(1-ns)) however many coefficients are
+  // used.  Take the smallest count that is within 30% of that floor (or already below the
+  // arithmetic's own resolution): ns+2 at sigma=2, the degree the reference tables also use
+  // (V/include/cufinufft/contrib/ker_horner_allw_loop.inc), instead of paying for 24.
+  const double floor_tol = is_double ? 2e-15 : 1.5e-8;
   double tmp[MAX_NCOEF_H];
-  int nc_used = MAX_NCOEF_H;
+  double err[MAX_NCOEF_H + 1];
   for (int nc = 4; nc <= MAX_NCOEF_H; nc++) {
-    double worst = 0.0;
-    for (int j = 0; j < ns; j++) worst = std::max(worst, fit_interval(ns, beta, j, nc, tmp));
-    if (worst <= tol) { nc_used = nc; break; }
+    err[nc] = 0.0;
+    for (int j = 0; j < ns; j++) err[nc] = std::max(err[nc], fit_interval(ns, beta, j, nc, tmp));
   }
+  double best = err[4];
+  for (int nc = 5; nc <= MAX_NCOEF_H; nc++) best = std::min(best, err[nc]);
+  int nc_used = MAX_NCOEF_H;
+  for (int nc = 4; nc <= MAX_NCOEF_H; nc++)
+    if (err[nc] <= std::max(1.3 * best, floor_tol)) { nc_used = nc; break; }
   std::memset(coef, 0, sizeof(double) * MAX_NCOEF_H * 16);
   for (int j = 0; j < ns; j++) {
     fit_interval(ns, beta, j, nc_used, tmp);

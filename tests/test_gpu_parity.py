@@ -1,0 +1,292 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libb200nufft.so (plan interface or b2n_run) and is compared with
+  * the recorded outputs of the unmodified reference cuFINUFFT (tests/golden),
+  * the CPU oracle (float64 restatement) on seeded mid-size inputs,
+  * the reference library itself when oracle/_ref travelled to the box,
+  * a float64 direct NUDFT,
+with the contract tolerance: relative l2 <= 2*eps (+ fp32 rounding floor), written in
+golden/cases.py::tolerance."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import ref_cufinufft as ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import cases as G  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(HERE, "golden", "ref_cufinufft_golden.npz")
+
+
+def T(a, dev="cuda"):
+    return torch.as_tensor(np.ascontiguousarray(a), device=dev)
+
+
+def run_plan(typ, dim, nm, pts, tgt, data, eps, iflag, dbl, **opts):
+    from jax_finufft_b200.plan import Plan
+
+    p = Plan(typ, dim if typ == 3 else nm, n_trans=data.shape[0], eps=eps, isign=iflag,
+             dtype="complex128" if dbl else "complex64", **opts)
+    p.setpts(*([T(x) for x in pts] + [None] * (3 - dim)), *([T(s) for s in tgt] + [None] * (3 - len(tgt))))
+    out = p.execute(T(data)).cpu().numpy()
+    info = p.info()
+    p.destroy()
+    return out, info
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3])
+@pytest.mark.parametrize("case", G.CASES, ids=[c[0] for c in G.CASES])
+def test_vs_reference_golden(case, method):
+    """ours vs recorded reference cuFINUFFT outputs, every gpu_method value the FFI can pass
+    (the reference rejects some method/type pairs; we accept 0-3 everywhere)."""
+    name, typ, dim, nm, M, N, eps, dbl, iflag, ntr, sigma, modeord = case
+    blob = np.load(GOLDEN)
+    gold = blob[name]
+    inp = G.make_inputs(case)
+    out, info = run_plan(typ, dim, nm, inp["pts"], inp["tgt"], inp["data"], eps, iflag, dbl,
+                         upsampfac=sigma, modeord=modeord, gpu_method=method)
+    assert out.shape == gold.shape
+    err = oracle.relerr(out, gold)
+    assert err < G.tolerance(case), (name, method, err)
+
+
+@pytest.mark.parametrize("case", G.CASES, ids=[c[0] for c in G.CASES])
+def test_not_worse_than_reference_vs_nudft(case):
+    """Yardstick of SURVEY.md §8c: our distance to the float64 NUDFT must not exceed the
+    reference's own (recorded) distance by more than rounding."""
+    name, typ, dim, nm, M, N, eps, dbl, iflag, ntr, sigma, modeord = case
+    blob = np.load(GOLDEN)
+    ref_err = float(blob[name + "__ref_vs_nudft"])
+    inp = G.make_inputs(case)
+    out, _ = run_plan(typ, dim, nm, inp["pts"], inp["tgt"], inp["data"], eps, iflag, dbl, upsampfac=sigma, modeord=modeord)
+    pts = [p.astype(np.float64) for p in inp["pts"]]
+    truth = []
+    for t in range(ntr):
+        d = inp["data"][t].astype(np.complex128)
+        if typ == 1:
+            truth.append(oracle.dirft1(nm, d, *pts, iflag=iflag, modeord=modeord))
+        elif typ == 2:
+            truth.append(oracle.dirft2(d, *pts, iflag=iflag, modeord=modeord))
+        else:
+            truth.append(oracle.dirft3(d, pts, [s.astype(np.float64) for s in inp["tgt"]], iflag=iflag))
+    err = oracle.relerr(out, np.stack(truth))
+    assert err < 1.5 * ref_err + (1e-14 if dbl else 1e-6), (name, err, ref_err)
+    assert err < 20 * eps + (0 if dbl else 2e-6)   # the reference's own checktol/tol ratio
+
+
+MID = [  # (dim, n_modes x-fastest, M, eps, double)
+    (1, (5000,), 30000, 1e-6, False),
+    (2, (200, 180), 100000, 1e-5, False),
+    (2, (128, 96), 60000, 1e-6, False),
+    (3, (48, 40, 36), 200000, 1e-6, False),
+    (3, (30, 32, 34), 100000, 1e-4, False),
+    (3, (24, 20, 28), 50000, 1e-3, False),
+    (2, (100, 90), 50000, 1e-11, True),
+    (3, (24, 20, 28), 50000, 1e-9, True),
+]
+
+
+@pytest.mark.parametrize("dim,nm,M,eps,dbl", MID, ids=[f"{d}d_{e:g}_{'d' if b else 'f'}" for d, _, _, e, b in MID])
+def test_mid_size_vs_oracle_and_live_reference(dim, nm, M, eps, dbl):
+    rng = np.random.default_rng(42 + dim)
+    rd, cd = (np.float64, np.complex128) if dbl else (np.float32, np.complex64)
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(rd) for _ in range(dim)]
+    c = (rng.uniform(-1, 1, (2, M)) + 1j * rng.uniform(-1, 1, (2, M))).astype(cd)
+    fk = (rng.uniform(-1, 1, (2,) + nm[::-1]) + 1j * rng.uniform(-1, 1, (2,) + nm[::-1])).astype(cd)
+    tol = 2 * eps + (2e-14 if dbl else 1.5e-6)
+    p64 = [p.astype(np.float64) for p in pts]
+    prec = 0 if dbl else 1
+    f, info = run_plan(1, dim, nm, pts, [], c, eps, 1, dbl)
+    assert oracle.relerr(f, oracle.nufft1(nm, c, *p64, eps=eps, iflag=1, prec=prec)) < tol
+    c2, _ = run_plan(2, dim, nm, pts, [], fk, eps, -1, dbl)
+    assert oracle.relerr(c2, oracle.nufft2(fk, *p64, eps=eps, iflag=-1, prec=prec)) < tol
+    if ref.available():
+        tp = [T(p) for p in pts] + [None] * (3 - dim)
+        r = ref.RefPlan(1, nm, n_trans=2, eps=eps, isign=1, dtype="complex128" if dbl else "complex64").setpts(*tp)
+        fr = r.execute(T(c)).cpu().numpy()
+        r.destroy()
+        assert oracle.relerr(f, fr) < tol
+        r = ref.RefPlan(2, nm, n_trans=2, eps=eps, isign=-1, dtype="complex128" if dbl else "complex64").setpts(*tp)
+        cr = r.execute(T(fk)).cpu().numpy()
+        r.destroy()
+        assert oracle.relerr(c2, cr) < tol
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_type3_mid_vs_oracle(dim):
+    rng = np.random.default_rng(7)
+    M, N, eps = 40000, 30000, 1e-6
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(dim)]
+    tgt = [rng.uniform(-40, 40, N).astype(np.float32) + (3.0 if d == 0 else 0.0) for d in range(dim)]
+    c = (rng.uniform(-1, 1, (2, M)) + 1j * rng.uniform(-1, 1, (2, M))).astype(np.complex64)
+    f, info = run_plan(3, dim, (), pts, tgt, c, eps, -1, False, upsampfac=2.0)
+    fo = oracle.nufft3(c, [p.astype(np.float64) for p in pts], [s.astype(np.float64) for s in tgt], eps=eps, iflag=-1, prec=1)
+    assert oracle.relerr(f, fo) < 2 * eps + 4e-6   # float type 3: phases at |s x| ~ 130 rad cost ~1e-6 (ops_test.py:120 uses 1e-3)
+
+
+def test_binsort_contract_vs_oracle():
+    """histogram, exclusive-scan offsets and per-bin point SETS must match;
+    the order inside a bin is unspecified in the reference (atomicAdd ranks)."""
+    from jax_finufft_b200.plan import Plan
+
+    rng = np.random.default_rng(11)
+    M, nm = 300000, (40, 36, 30)
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(3)]
+    pts[0][:5] = [-np.pi, np.pi, np.nextafter(np.float32(np.pi), np.float32(0)), 0.0, 3 * np.pi]
+    p = Plan(1, nm, eps=1e-6).setpts(*[T(x) for x in pts])
+    info = p.info()
+    idx, bstart = p.sort_arrays()
+    idx, bstart = idx.cpu().numpy(), bstart.cpu().numpy()
+    p.destroy()
+    nf = [int(info.nf[d]) for d in range(3)]
+    bins = [int(info.binsize[d]) for d in range(3)]
+    binid, hist = oracle.binsort([x.astype(np.float64) for x in pts], nf, bins, prec=1)
+    assert bstart[0] == 0 and bstart[-1] == M
+    assert (np.diff(bstart) == hist).all()                       # histogram + offsets
+    assert (np.sort(idx) == np.arange(M)).all()                  # a permutation
+    assert (binid[idx] == np.repeat(np.arange(hist.size), hist)).all()   # per-bin sets
+
+
+def test_edge_cases_empty_single_far_and_clustered():
+    from jax_finufft_b200.plan import Plan
+
+    nm = (16, 12, 10)
+    # M = 0: type 1 gives zeros, type 2 gives an empty vector
+    p = Plan(1, nm, eps=1e-6).setpts(*[torch.empty(0, device="cuda") for _ in range(3)])
+    f = p.execute(torch.empty((1, 0), dtype=torch.complex64, device="cuda"))
+    assert f.shape == (1, 10, 12, 16) and float(f.abs().max()) == 0.0
+    p.destroy()
+    # M = 1 at the periodic seam, points far outside [-3pi, 3pi], all points in one fine cell
+    rng = np.random.default_rng(0)
+    for pts in ([np.array([np.pi], np.float32)] * 3,
+                [rng.uniform(-300, 300, 2000).astype(np.float32) for _ in range(3)],
+                [(1e-3 * rng.uniform(-1, 1, 5000) - np.pi).astype(np.float32) for _ in range(3)]):
+        M = pts[0].size
+        c = (rng.uniform(-1, 1, (1, M)) + 1j * rng.uniform(-1, 1, (1, M))).astype(np.complex64)
+        f, _ = run_plan(1, 3, nm, pts, [], c, 1e-6, 1, False)
+        fo = oracle.nufft1(nm, c, *[x.astype(np.float64) for x in pts], eps=1e-6, prec=1)
+        tol = 2e-6 + 1.5e-6 if np.abs(pts[0]).max() < 10 else 1e-4   # |x|~300 in fp32: the fold itself loses 5 digits
+        assert oracle.relerr(f, fo) < tol
+        fk = (rng.uniform(-1, 1, (1,) + nm[::-1]) + 1j * rng.uniform(-1, 1, (1,) + nm[::-1])).astype(np.complex64)
+        c2, _ = run_plan(2, 3, nm, pts, [], fk, 1e-6, -1, False)
+        co = oracle.nufft2(fk, *[x.astype(np.float64) for x in pts], eps=1e-6, prec=1)
+        assert oracle.relerr(c2, co) < tol
+
+
+def test_many_transforms_more_than_one_batch_and_repeated_setpts():
+    """ntransf > batch (impl.h:123-127) and two setpts with different M on one plan
+    (V/test/cuda/cufinufft2d1nupts_test.cu -- the n_tot>1 pattern of run_nufft)."""
+    from jax_finufft_b200.plan import Plan
+
+    rng = np.random.default_rng(9)
+    nm, ntr = (40, 30), 11
+    p = Plan(1, nm, n_trans=ntr, eps=1e-5, gpu_maxbatchsize=4)
+    for M in (7000, 2500):
+        pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(2)]
+        c = (rng.uniform(-1, 1, (ntr, M)) + 1j * rng.uniform(-1, 1, (ntr, M))).astype(np.complex64)
+        p.setpts(T(pts[0]), T(pts[1]))
+        f = p.execute(T(c)).cpu().numpy()
+        fo = oracle.nufft1(nm, c, *[x.astype(np.float64) for x in pts], eps=1e-5, prec=1)
+        assert oracle.relerr(f, fo) < 2e-5 + 1.5e-6
+    p.destroy()
+
+
+@pytest.mark.parametrize("kem,sort", [(0, 1), (1, 0), (0, 0)])
+def test_kerevalmeth_direct_and_unsorted(kem, sort):
+    rng = np.random.default_rng(13)
+    nm, M = (20, 24, 18), 20000
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(3)]
+    c = (rng.uniform(-1, 1, (1, M)) + 1j * rng.uniform(-1, 1, (1, M))).astype(np.complex64)
+    f, _ = run_plan(1, 3, nm, pts, [], c, 1e-5, 1, False, gpu_kerevalmeth=kem, gpu_sort=sort)
+    fo = oracle.nufft1(nm, c, *[x.astype(np.float64) for x in pts], eps=1e-5, kerevalmeth=kem, prec=1)
+    assert oracle.relerr(f, fo) < 2e-5 + 1.5e-6
+
+
+def test_spreadinterponly_matches_oracle_spread():
+    """gpu_spreadinterponly=1 (impl.h:115-117): the output IS the fine grid."""
+    rng = np.random.default_rng(17)
+    nf, M = (64, 48, 40), 50000
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(3)]
+    c = (rng.uniform(-1, 1, (1, M)) + 1j * rng.uniform(-1, 1, (1, M))).astype(np.complex64)
+    fw, info = run_plan(1, 3, nf, pts, [], c, 1e-6, 1, False, gpu_spreadinterponly=1)
+    fo = oracle.spread([x.astype(np.float64) for x in pts], c[0], nf, info.ns, info.beta, prec=1)
+    assert oracle.relerr(fw[0], fo) < 1e-6
+    g = (rng.uniform(-1, 1, (1,) + nf[::-1]) + 1j * rng.uniform(-1, 1, (1,) + nf[::-1])).astype(np.complex64)
+    ci, _ = run_plan(2, 3, nf, pts, [], g, 1e-6, -1, False, gpu_spreadinterponly=1)
+    co = oracle.interp([x.astype(np.float64) for x in pts], g[0], info.ns, info.beta, prec=1)
+    assert oracle.relerr(ci[0], co) < 1e-6
+
+
+def test_run_host_entry_point():
+    """b2n_run_host: the C-ABI call a foreign-language host makes with HOST buffers."""
+    from jax_finufft_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(21)
+    n_tot, ntr, M, nk = 2, 3, 4000, (18, 14, 10)
+    pts = [np.ascontiguousarray(rng.uniform(-np.pi, np.pi, (n_tot, M)).astype(np.float32)) for _ in range(3)]
+    c = np.ascontiguousarray((rng.uniform(-1, 1, (n_tot, ntr, M)) + 1j * rng.uniform(-1, 1, (n_tot, ntr, M))).astype(np.complex64))
+    out = np.zeros((n_tot, ntr) + nk[::-1], np.complex64)
+    o = _lib.default_opts()
+    o.upsampfac = 2.0
+    n_k = (C.c_int64 * 3)(*nk)
+    pp = (C.c_void_p * 3)(*[p.ctypes.data for p in pts])
+    rc = L.b2n_run_host(1, 3, 0, 1e-6, 1, n_tot, ntr, M, n_k, C.byref(o), c.ctypes.data, pp, None, out.ctypes.data)
+    assert rc == 0
+    for i in range(n_tot):
+        fo = oracle.nufft1(nk, c[i], *[p[i].astype(np.float64) for p in pts], eps=1e-6, prec=1)
+        assert oracle.relerr(out[i], fo) < 2e-6 + 1.5e-6
+
+
+@pytest.mark.parametrize("typ", [1, 2])
+def test_full_size_properties_c3(typ):
+    """BASELINE config C3 (3-D, M=1e8, N=256^3, eps=1e-6, c64): size-independent checks --
+    a random sample of outputs against a float64 direct NUDFT, and the adjoint identity
+    <nufft1(c), f> = <c, nufft2(f)> (type 1 / type 2 with the same points and opposite iflag
+    are exact adjoints), which exercises every point and every mode."""
+    from jax_finufft_b200.plan import Plan
+
+    M, nm, eps = 10 ** 8, (256, 256, 256), 1e-6
+    g = torch.Generator(device="cuda").manual_seed(1)
+    pts = [(torch.rand(M, device="cuda", generator=g) * 2 - 1) * np.pi for _ in range(3)]
+    c = torch.complex(torch.rand(M, device="cuda", generator=g) * 2 - 1, torch.rand(M, device="cuda", generator=g) * 2 - 1)[None]
+    f = torch.complex(torch.rand(nm, device="cuda", generator=g) * 2 - 1, torch.rand(nm, device="cuda", generator=g) * 2 - 1)[None]
+    p1 = Plan(1, nm, eps=eps, isign=1).setpts(*pts)
+    F = p1.execute(c)
+    p1.destroy()
+    p2 = Plan(2, nm, eps=eps, isign=-1).setpts(*pts)
+    Cc = p2.execute(f)
+    p2.destroy()
+    lhs = torch.sum(F.to(torch.complex128) * f.to(torch.complex128).conj())
+    rhs = torch.sum(c.to(torch.complex128) * Cc.to(torch.complex128).conj())
+    assert abs(lhs - rhs) / abs(lhs) < 2e-5
+    rng = np.random.default_rng(3)
+    if typ == 1:   # 24 random modes, each an M-term sum in float64
+        ks = rng.integers(-128, 128, size=(24, 3))
+        x64 = [p.to(torch.float64) for p in pts]
+        c64 = c[0].to(torch.complex128)
+        errs = []
+        for kx, ky, kz in ks:
+            ph = kx * x64[0] + ky * x64[1] + kz * x64[2]
+            truth = torch.sum(c64 * torch.polar(torch.ones_like(ph), ph))
+            got = F[0, kz + 128, ky + 128, kx + 128]
+            errs.append(abs(complex(got) - complex(truth)))
+        scale = float(torch.sqrt(torch.mean(torch.abs(F) ** 2)))
+        assert max(errs) / scale < 2e-5
+    else:          # 4000 random points, each a 256^3-term sum (separable in float64)
+        js = torch.as_tensor(rng.integers(0, M, size=4000), device="cuda")
+        k = torch.arange(-128, 128, device="cuda", dtype=torch.float64)
+        ex = [torch.polar(torch.ones(4000, 256, device="cuda", dtype=torch.float64), -pts[d][js].to(torch.float64)[:, None] * k[None]) for d in range(3)]
+        f128 = f[0].to(torch.complex128)             # [z, y, x]
+        t = torch.einsum("zyx,jx->jzy", f128, ex[0])
+        t = torch.einsum("jzy,jy->jz", t, ex[1])
+        truth = torch.einsum("jz,jz->j", t, ex[2])
+        got = Cc[0][js].to(torch.complex128)
+        assert float(torch.linalg.norm(got - truth) / torch.linalg.norm(truth)) < 2e-5
