@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 NUFFT backend (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3_t1|c3_t2|c3_t1_clustered]
+    python bench.py --impl reference ...        # CPU arm: the oracle port on the host cores
+
+A *step* is one pass of the hot path over one batch of synthetic input: one custom call as
+jax-finufft issues it (run_nufft, lib/kernels.cc.cu:25-92) = bin-sort the points (setpts) +
+execute one 3-D transform.  Default workload = BASELINE.json configs[2]: 3-D type 1, M=1e8
+uniform random points, N=256^3 modes, eps=1e-6, complex64 (``c3_t1``); type 2 on the same
+points and the clustered distribution are measured too and reported under ``also``.
+
+N>1 (torchrun): the path shards over independent transforms (n_tot / vmapped batch): every
+rank runs its own M=1e8 transform on its own GPU, no data-path collective -> weak scaling;
+``value`` = N*M / max-over-ranks time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    #  name              type  M      N (JAX order)     eps   dist
+    "c3_t1": (1, 10 ** 8, (256, 256, 256), 1e-6, "uniform"),
+    "c3_t2": (2, 10 ** 8, (256, 256, 256), 1e-6, "uniform"),
+    "c3_t1_clustered": (1, 10 ** 8, (256, 256, 256), 1e-6, "clustered"),
+    "c3_t2_clustered": (2, 10 ** 8, (256, 256, 256), 1e-6, "clustered"),
+    "small_t1": (1, 10 ** 6, (64, 64, 64), 1e-6, "uniform"),   # dev only
+}
+METRIC = "NU points/sec, 3-D type-{t} (eps=1e-6, complex64, M=1e8, N=256^3), setpts+execute per step"
+UNIT = "NU points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3_t1", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="skip also/e2e/cpu_baseline legs (profiling runs)")
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="points per CPU-baseline step")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- synthetic inputs
+def make_points(M, dist, nf, device, seed):
+    """uniform = U[-pi,pi)^3 (V/perftest/cuda/cuperftest.cu:197-220);
+    clustered = iid uniform in the corner box [-pi, -pi + 8h)^3, h = 2pi/nf (8 fine cells per dim)."""
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    pts = []
+    for d in range(3):
+        u = torch.rand(M, device=device, generator=g)
+        if dist == "uniform":
+            pts.append((u * 2 - 1) * np.pi)
+        else:
+            pts.append(-np.pi + u * (8 * 2 * np.pi / nf))
+    return pts, g
+
+
+def make_complex(shape, device, g):
+    import torch
+
+    return torch.complex(torch.rand(shape, device=device, generator=g) * 2 - 1,
+                         torch.rand(shape, device=device, generator=g) * 2 - 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_port_rate(typ, M_full, nm, eps, sample, steps, warmup):
+    """Times oracle/nufft_oracle.c (OpenMP, all host threads) on a bounded sample: the full
+    N=256^3 pipeline on `sample` points per step, plus one tiny-M run for the M-independent cost
+    (FFT + deconvolve), extrapolated linearly in M to the full workload."""
+    import oracle
+
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-np.pi, np.pi, size=(3, sample))
+    nmx = tuple(nm[::-1])
+    if typ == 1:
+        d = rng.uniform(-1, 1, sample) + 1j * rng.uniform(-1, 1, sample)
+        run = lambda n: oracle.nufft1(nmx, d[:n], *x[:, :n], eps=eps, prec=1)
+    else:
+        d = rng.uniform(-1, 1, nm) + 1j * rng.uniform(-1, 1, nm)
+        run = lambda n: oracle.nufft2(d, *x[:, :n], eps=eps, prec=1)
+    t0 = time.perf_counter(); run(1000); t_fixed = time.perf_counter() - t0
+    for _ in range(max(0, warmup - 1)):
+        run(sample)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); run(sample); ts.append(time.perf_counter() - t0)
+    t_step = statistics.mean(ts)
+    per_pt = max(t_step - t_fixed, 1e-9) / sample
+    t_full = t_fixed + per_pt * M_full
+    return {
+        "value": M_full / t_full, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+        "sample": (f"oracle/nufft_oracle.c (float64 restatement, OpenMP x{oracle.num_threads()}): {steps} steps of the full "
+                   f"N=256^3 pipeline on {sample} points ({t_step:.2f} s/step, of which {t_fixed:.2f} s is M-independent "
+                   f"FFT/deconvolve), extrapolated linearly in M to M={M_full}: {t_full:.1f} s; the reference CPU FINUFFT "
+                   "(xsimd+FFTW) cannot be built offline (SURVEY.md §8c)"),
+        "ms_per_step_extrapolated": t_full * 1e3,
+    }
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    typ, M, nm, eps, dist = WORKLOADS[a.workload]
+    steps = max(1, min(a.steps, 5))
+    cb = cpu_port_rate(typ, M, nm, eps, a.cpu_sample, steps, min(a.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC.format(t=typ), "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": steps, "warmup": min(a.warmup, 1), "ms_per_step": cb["ms_per_step_extrapolated"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": a.workload, "type": typ, "M": M, "N": list(nm), "eps": eps, "points": dist},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import jax_finufft_b200 as J
+    from jax_finufft_b200 import _lib
+    from jax_finufft_b200.plan import Plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU path for --impl ours")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step, K, W):
+        for _ in range(W):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.b2n_launch_count()
+        e0.record()
+        for _ in range(K):
+            step()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / K, (L.b2n_launch_count() - n0)
+
+    def workload(name):
+        typ, M, nm, eps, distn = WORKLOADS[name]
+        nf = 2 * nm[-1]
+        pts, g = make_points(M, distn, nf, dev, seed=1 + rank)
+        data = make_complex((M,) if typ == 1 else nm, dev, g)
+        # JAX order: the LAST point array is the backend's x (lowering.py:96-105)
+        if typ == 1:
+            step = lambda: J.nufft1(nm, data, *pts, eps=eps, iflag=1)
+        else:
+            step = lambda: J.nufft2(data, *pts, eps=eps, iflag=-1)
+        return typ, M, nm, eps, distn, pts, data, step
+
+    typ, M, nm, eps, distn, pts, data, step = workload(a.workload)
+    nftot = 1
+    for n in nm:
+        nftot *= 2 * n
+
+    # ---- headline: device-resident inputs, K steps, device events, max over ranks
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches = timed(step, a.steps, a.warmup)
+    clocks = sampler.stop() if sampler else None
+    value = world * M / (ms * 1e-3)
+
+    line = {
+        "metric": METRIC.format(t=typ), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": a.workload, "type": typ, "M_per_gpu": M, "N": list(nm), "eps": eps, "points": distn,
+                   "seed": "1+rank", "step": "b2n_run = setpts (bin-sort) + execute, plan cached",
+                   "l2": "inputs (2.0 GB points+strengths, 1.07 GB fine grid) exceed the 126 MB L2; no explicit flush",
+                   "sharding": "independent transforms per GPU (n_tot split), no data-path collective" if world > 1 else "single GPU"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+    if not a.no_extras:
+        # ---- per-stage device times + roofline of the dominant kernel (CUDA events on the plan's
+        # stream, inside the library: b2n_plan_timings)
+        if rank == 0:
+            p = Plan(typ, nm[::-1], eps=eps, isign=1 if typ == 1 else -1, debug=1)
+            out = None
+            KR = max(3, min(a.steps, 5))
+            for it in range(KR + 1):
+                p.setpts(pts[2], pts[1], pts[0])
+                out = p.execute(data[None] if typ == 1 else data[None], out=out)
+                if it == 0:
+                    p.timings()  # drop warm-up
+            st = {k: v / KR for k, v in p.timings().items()}
+            p.destroy()
+            del out
+            kern = "spread" if typ == 1 else "interp"
+            alg_bytes = (4 * 3 + 12) * M + 8 * nftot          # (4d+12)*M + 8*nf
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            achieved = alg_bytes / (st[kern] * 1e-3) / 1e9
+            traffic = None
+            tf = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tf):
+                traffic = json.load(open(tf)).get(f"{a.workload}:{kern}")
+            line["roofline"] = {"bound": "hbm", "kernel": "k_spread3d<float,7>" if typ == 1 else "k_interp<float,7,3>",
+                                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                                "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel_ms": st[kern],
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                                "note": "3-D ns=7 spread/interp is shared-memory-bound (343 complex cell updates per point), "
+                                        "see DESIGN.md; HBM fraction reported as the contract asks"}
+            line["stages_ms"] = st
+        barrier()
+
+        # ---- e2e: the C-ABI call with HOST buffers (pinned), H2D + D2H inside the timed region
+        host_pts = [torch.empty(M, dtype=torch.float32).pin_memory() for _ in range(3)]
+        for h, d_ in zip(host_pts, pts):
+            h.copy_(d_)
+        host_in = torch.empty(data.shape, dtype=torch.complex64).pin_memory()
+        host_in.copy_(data)
+        out_shape = nm if typ == 1 else (M,)
+        host_out = torch.empty(out_shape, dtype=torch.complex64).pin_memory()
+        o = _lib.default_opts()
+        o.upsampfac = 2.0
+        n_k = (C.c_int64 * 3)(*nm[::-1])
+        pp = (C.c_void_p * 3)(host_pts[2].data_ptr(), host_pts[1].data_ptr(), host_pts[0].data_ptr())
+
+        def e2e_step():
+            rc = L.b2n_run_host(typ, 3, 0, eps, 1 if typ == 1 else -1, 1, 1, M, n_k, C.byref(o),
+                                C.c_void_p(host_in.data_ptr()), pp, None, C.c_void_p(host_out.data_ptr()))
+            if rc > 1:
+                raise RuntimeError(f"b2n_run_host failed: {rc}")
+
+        KE = max(2, min(a.steps, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(KE):
+            e2e_step()
+        torch.cuda.synchronize()
+        t_e2e = max_over_ranks((time.perf_counter() - t0) / KE)
+        h2d = sum(h.numel() * 4 for h in host_pts) + host_in.numel() * 8
+        d2h = host_out.numel() * 8
+        line["e2e"] = {"value": world * M / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": t_e2e * 1e3, "steps": KE, "api": "b2n_run_host (include/b200nufft.h), pinned host buffers"}
+        del host_pts, host_in, host_out
+
+        # ---- the other halves of the BASELINE metric (type 2; clustered points), fewer steps
+        also = {}
+        del pts, data, step
+        torch.cuda.empty_cache()
+        for name in ("c3_t1", "c3_t2", "c3_t1_clustered", "c3_t2_clustered"):
+            if name == a.workload or not a.workload.startswith("c3"):
+                continue
+            w = workload(name)
+            ms2, _ = timed(w[-1], 3, 2)
+            also[name] = {"value": world * w[1] / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "steps": 3}
+            del w
+            torch.cuda.empty_cache()
+        line["also"] = also
+
+        # ---- CPU baseline: the oracle port on the host cores (rank 0, N=1 only)
+        if rank == 0 and world == 1:
+            line["cpu_baseline"] = cpu_port_rate(typ, M, nm, eps, a.cpu_sample, 2, 1)
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)

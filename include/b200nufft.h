@@ -100,6 +100,9 @@ int b2n_plan_info_get(b2n_plan plan, b2n_plan_info *info);
  * Device pointers owned by the plan, valid until the next setpts/destroy. */
 int b2n_plan_sort_get(b2n_plan plan, const int32_t **idx, const int32_t **bin_start,
                       int64_t *nbins);
+/* Copies the same two arrays into caller-owned DEVICE buffers (idx_out[M], bin_start_out[nbins+1])
+ * on the plan's stream and synchronises it. */
+int b2n_plan_sort_copy(b2n_plan plan, int32_t *idx_out, int32_t *bin_start_out);
 
 /* replaces run_nufft<ndim,T,type> (lib/kernels.cc.cu:25-92) -- the one call the XLA-FFI shim
  * makes per custom call: plan once, loop n_tot point sets {setpts, execute}, no retained
@@ -140,6 +143,8 @@ void b2n_fseries(int64_t nf, int ns, double beta, double *fwkerhalf /* nf/2+1 */
 int b2n_horner_table(int ns, double beta, int is_double, double *coef /* 24*16 */);
 void b2n_default_binsize(int dim, int ns, int is_double, int type, int *binsize3);
 const char *b2n_version(void);
+/* Kernels of this library launched so far by the calling process (bench.py: gpu_launches). */
+unsigned long long b2n_launch_count(void);
 
 #ifdef __cplusplus
 }

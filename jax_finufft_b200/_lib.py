@@ -51,9 +51,9 @@ class B2nPlanInfo(C.Structure):
 
 EXPORTED = [
     "b2n_default_opts", "b2n_makeplan", "b2n_setpts", "b2n_execute", "b2n_destroy",
-    "b2n_plan_info_get", "b2n_plan_sort_get", "b2n_run", "b2n_run_host", "b2n_cache_clear",
+    "b2n_plan_info_get", "b2n_plan_sort_get", "b2n_plan_sort_copy", "b2n_run", "b2n_run_host", "b2n_cache_clear",
     "b2n_plan_timings", "b2n_setup_spreader", "b2n_next235beven", "b2n_set_nf_type12",
-    "b2n_fseries", "b2n_horner_table", "b2n_default_binsize", "b2n_version",
+    "b2n_fseries", "b2n_horner_table", "b2n_default_binsize", "b2n_version", "b2n_launch_count",
 ]
 
 
@@ -77,6 +77,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         vp, i64, dbl, ci = C.c_void_p, C.c_int64, C.c_double, C.c_int
         L.b2n_version.restype = C.c_char_p
+        L.b2n_launch_count.restype = C.c_ulonglong
         L.b2n_default_opts.argtypes = [C.POINTER(B2nOpts)]
         L.b2n_default_opts.restype = None
         L.b2n_makeplan.argtypes = [ci, ci, C.POINTER(i64), ci, ci, dbl, ci, C.POINTER(vp), C.POINTER(B2nOpts)]
@@ -85,6 +86,7 @@ def lib():
         L.b2n_destroy.argtypes = [vp]
         L.b2n_plan_info_get.argtypes = [vp, C.POINTER(B2nPlanInfo)]
         L.b2n_plan_sort_get.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
+        L.b2n_plan_sort_copy.argtypes = [vp, vp, vp]
         L.b2n_plan_timings.argtypes = [vp, C.POINTER(dbl)]
         L.b2n_run.argtypes = [ci, ci, ci, vp, dbl, ci, i64, ci, i64, C.POINTER(i64), C.POINTER(B2nOpts), vp,
                               C.POINTER(vp), C.POINTER(vp), vp]

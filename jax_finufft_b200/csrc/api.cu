@@ -11,6 +11,8 @@
 
 namespace b2n {
 
+unsigned long long g_launch_count = 0;
+
 // ------------------------------------------------------------------------------------ utilities
 struct StageTimer {
   cudaEvent_t a = nullptr, b = nullptr;
@@ -170,7 +172,7 @@ int Plan<T>::init(int type_, int dim_, const int64_t *n_modes, int iflag_, int n
     if (int e = alloc_grid()) return e;
   }
   if (opts.debug)
-    printf("[b200nufft] plan: type %d dim %d %s eps=%.3g sigma=%.3g ns=%d beta=%.4g ncoef=%d method=%s "
+    fprintf(stderr, "[b200nufft] plan: type %d dim %d %s eps=%.3g sigma=%.3g ns=%d beta=%.4g ncoef=%d method=%s "
            "bins=(%d,%d,%d) nf=(%ld,%ld,%ld) batch=%d\n",
            type, dim, is_double ? "f64" : "f32", eps, sigma, ns, beta, ncoef, method == 2 ? "tile" : "GM",
            bin[0], bin[1], bin[2], (long)nf[0], (long)nf[1], (long)nf[2], batch);
@@ -256,7 +258,7 @@ int Plan<T>::setpts3(int64_t M, const T *x, const T *y, const T *z, int64_t N, c
   }
   if (opts.debug)
     for (int d = 0; d < dim; d++)
-      printf("[b200nufft] t3 dim %d: X=%.3g C=%.3g S=%.3g D=%.3g gam=%g nf=%ld h=%.3g\n", d, t3X[d],
+      fprintf(stderr, "[b200nufft] t3 dim %d: X=%.3g C=%.3g S=%.3g D=%.3g gam=%g nf=%ld h=%.3g\n", d, t3X[d],
              t3C[d], t3S[d], t3D[d], t3gam[d], (long)nf[d], t3h[d]);
   // outer grid: spread-only plan geometry + its own fine grid (batch * nf)
   nftot = 1;
@@ -525,6 +527,8 @@ extern "C" {
 
 const char *b2n_version(void) { return "b200nufft 0.1 (sm_100a)"; }
 
+unsigned long long b2n_launch_count(void) { return g_launch_count; }
+
 void b2n_default_opts(b2n_opts *o) {  // defaults of V/src/cuda/cufinufft.cu:133-152
   std::memset(o, 0, sizeof(*o));
   o->modeord = 0;
@@ -617,6 +621,21 @@ int b2n_plan_info_get(b2n_plan plan, b2n_plan_info *info) {
 int b2n_plan_sort_get(b2n_plan plan, const int32_t **idx, const int32_t **bin_start, int64_t *nbins) {
   if (!plan) return B2N_ERR_PLAN_NOTVALID;
   return reinterpret_cast<PlanBase *>(plan)->sort_get(idx, bin_start, nbins);
+}
+
+int b2n_plan_sort_copy(b2n_plan plan, int32_t *idx_out, int32_t *bin_start_out) {
+  if (!plan) return B2N_ERR_PLAN_NOTVALID;
+  PlanBase *p = reinterpret_cast<PlanBase *>(plan);
+  const int32_t *idx = nullptr, *bs = nullptr;
+  int64_t nb = 0;
+  if (int e = p->sort_get(&idx, &bs, &nb)) return e;
+  b2n_plan_info inf;
+  p->info(&inf);
+  cudaStream_t st = p->get_stream();
+  B2N_CUDA_OK(cudaMemcpyAsync(idx_out, idx, sizeof(int32_t) * (size_t)inf.M, cudaMemcpyDeviceToDevice, st));
+  B2N_CUDA_OK(cudaMemcpyAsync(bin_start_out, bs, sizeof(int32_t) * (size_t)(nb + 1), cudaMemcpyDeviceToDevice, st));
+  B2N_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
 }
 
 int b2n_plan_timings(b2n_plan plan, double *ms7) {

@@ -146,6 +146,10 @@ __device__ __forceinline__ void red_add(double2 *addr, double2 v) {
   atomicAdd(&addr->y, v.y);
 }
 
+// number of kernels of THIS library launched by the calling process (bench.py's gpu_launches)
+extern unsigned long long g_launch_count;
+#define B2N_LAUNCHED(n) (::b2n::g_launch_count += (n))
+
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace b2n

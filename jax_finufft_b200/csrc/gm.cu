@@ -107,7 +107,7 @@ static int launch_gm(Plan<T> &p, const cpx<T> *cin, cpx<T> *cout, const cpx<T> *
   a.dim = p.dim;
   a.ns = p.ns;
   dim3 grid((unsigned)cdiv(p.pts.M, 128), (unsigned)ntr);
-  k_gm<T, SPREAD><<<grid, 128, 0, p.stream>>>(a, p.tab);
+  k_gm<T, SPREAD><<<grid, 128, 0, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   return 0;
 }

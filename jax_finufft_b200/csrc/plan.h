@@ -31,6 +31,7 @@ struct PlanBase {
   virtual void info(b2n_plan_info *out) = 0;
   virtual int sort_get(const int32_t **idx, const int32_t **bin_start, int64_t *nbins) = 0;
   virtual void set_stream(cudaStream_t s) = 0;
+  virtual cudaStream_t get_stream() const = 0;
   bool is_double = false;
   double timings[7] = {0, 0, 0, 0, 0, 0, 0};
 };
@@ -88,6 +89,7 @@ template <typename T> struct Plan : PlanBase {
   void info(b2n_plan_info *out) override;
   int sort_get(const int32_t **idx, const int32_t **bin_start, int64_t *nbins) override;
   void set_stream(cudaStream_t s) override;
+  cudaStream_t get_stream() const override { return stream; }
 };
 
 // ---- stage launchers (one per .cu file) -------------------------------------------------------

@@ -119,9 +119,9 @@ int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t 
   const int nb = cdiv(n, SCAN_CH);
   int32_t *bsum = nullptr;
   if (int e = dev_alloc_t(&bsum, (size_t)nb + 1, st)) return e;
-  k_scan_blocks<<<nb, SCAN_T, 0, st>>>(in, out, n, bsum);
-  k_scan_bsum<<<1, 1024, 0, st>>>(bsum, nb, out + n);
-  k_scan_add<<<nb, SCAN_T, 0, st>>>(out, n, bsum);
+  k_scan_blocks<<<nb, SCAN_T, 0, st>>>(in, out, n, bsum);  B2N_LAUNCHED(1);
+  k_scan_bsum<<<1, 1024, 0, st>>>(bsum, nb, out + n);  B2N_LAUNCHED(1);
+  k_scan_add<<<nb, SCAN_T, 0, st>>>(out, n, bsum);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   dev_free(bsum, st);
   return 0;
@@ -254,7 +254,7 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   const int nblk = (int)std::min<int64_t>(std::max<int64_t>(cdiv(M, 256), 1), 148 * 16);
   const bool sorted = p.opts.gpu_sort != 0 || p.method != 1;
   if (!sorted) {
-    if (M > 0) k_fold_only<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.idx, ps.xs[0], ps.xs[1], ps.xs[2]);
+    if (M > 0) k_fold_only<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.idx, ps.xs[0], ps.xs[1], ps.xs[2]);  B2N_LAUNCHED(1);
     B2N_LAUNCH_OK();
     ps.sp_cap = 0;
     return 0;
@@ -284,19 +284,19 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   if (int e = dev_alloc_t(&pbin, (size_t)M, st)) return e;
   if (int e = dev_alloc_t(&prank, (size_t)M, st)) return e;
   B2N_CUDA_OK(cudaMemsetAsync(hist, 0, sizeof(int32_t) * nbins, st));
-  if (M > 0) k_bin_count<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, hist, pbin, prank);
+  if (M > 0) k_bin_count<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, hist, pbin, prank);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   if (int e = exclusive_scan_i32(hist, ps.bin_start, nbins, st)) return e;
   if (M > 0)
     k_bin_scatter<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.bin_start, pbin, prank, ps.idx,
-                                           ps.xs[0], ps.xs[1], ps.xs[2]);
+                                           ps.xs[0], ps.xs[1], ps.xs[2]);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   // subproblem list, entirely on device (the reference reads the total back and syncs,
   // V/src/cuda/3d/spread3d_wrapper.cu:479-487)
   const int nb_blk = cdiv(nbins, 256);
-  k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, ps.bin_start, p.maxsub, hist);
+  k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, ps.bin_start, p.maxsub, hist);  B2N_LAUNCHED(1);
   if (int e = exclusive_scan_i32(hist, ps.sp_off, nbins, st)) return e;
-  k_sp_fill<<<nb_blk, 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);
+  k_sp_fill<<<nb_blk, 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   dev_free(hist, st);
   dev_free(pbin, st);

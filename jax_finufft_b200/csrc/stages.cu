@@ -40,7 +40,7 @@ template <typename T> int compute_fseries(Plan<T> &p) {
     nmax = std::max(nmax, (int)p.nf[d] / 2 + 1);
   }
   dim3 grid(std::min(cdiv(nmax, 128), 1024), p.dim);
-  k_fseries<T><<<grid, 128, 0, p.stream>>>(qa, p.fwker[0], p.fwker[1], p.fwker[2]);
+  k_fseries<T><<<grid, 128, 0, p.stream>>>(qa, p.fwker[0], p.fwker[1], p.fwker[2]);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   return 0;
 }
@@ -109,7 +109,7 @@ template <typename T> int deconvolve(Plan<T> &p, const cpx<T> *fw, cpx<T> *fk, i
   for (int d = 0; d < 3; d++) { g.ms[d] = (int)p.ms[d]; g.nf[d] = (int)p.nf[d]; }
   dim3 grid((unsigned)cdiv(p.nmodes, 256), (unsigned)ntr);
   k_deconvolve<T><<<grid, 256, 0, p.stream>>>(g, fw, fk, p.fwker[0], p.fwker[1], p.fwker[2],
-                                              p.nmodes, p.nftot);
+                                              p.nmodes, p.nftot);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   return 0;
 }
@@ -160,7 +160,7 @@ template <typename T> int amplify(Plan<T> &p, cpx<T> *fw, const cpx<T> *fk, int 
   for (int d = 0; d < 3; d++) { g.ms[d] = (int)p.ms[d]; g.nf[d] = (int)p.nf[d]; }
   dim3 grid((unsigned)cdiv(p.nftot, 256), (unsigned)ntr);
   k_amplify<T><<<grid, 256, 0, p.stream>>>(g, fw, fk, p.fwker[0], p.fwker[1], p.fwker[2], p.nmodes,
-                                           p.nftot);
+                                           p.nftot);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   return 0;
 }
@@ -219,7 +219,7 @@ int t3_minmax(cudaStream_t st, int dim, int64_t M, const T *const *x, int64_t N,
   const int nb = 148 * 2;
   double *part = nullptr;
   if (int e = dev_alloc_t(&part, (size_t)6 * nb * 2, st)) return e;
-  k_minmax<T><<<dim3(nb, 6), 256, 0, st>>>(mm, part);
+  k_minmax<T><<<dim3(nb, 6), 256, 0, st>>>(mm, part);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   std::vector<double> h((size_t)6 * nb * 2);
   B2N_CUDA_OK(cudaMemcpyAsync(h.data(), part, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -329,8 +329,8 @@ template <typename T> int t3_prepare(Plan<T> &p, const T *const *x, const T *con
   a.prephase = p.prephase;
   a.deconv = p.deconv;
   a.sign = p.iflag >= 0 ? T(1) : T(-1);
-  if (a.M > 0) k_t3_sources<T><<<cdiv(a.M, 256), 256, 0, p.stream>>>(a);
-  if (a.N > 0) k_t3_targets<T><<<cdiv(a.N, 256), 256, 0, p.stream>>>(a);
+  if (a.M > 0) k_t3_sources<T><<<cdiv(a.M, 256), 256, 0, p.stream>>>(a);  B2N_LAUNCHED(1);
+  if (a.N > 0) k_t3_targets<T><<<cdiv(a.N, 256), 256, 0, p.stream>>>(a);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   return 0;
 }

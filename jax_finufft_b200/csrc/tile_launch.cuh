@@ -65,10 +65,10 @@ int launch_spread_ns(Plan<T> &p, const cpx<T> *c, const cpx<T> *prescale, cpx<T>
   dim3 grid((unsigned)p.pts.sp_cap, (unsigned)ntr);
   if constexpr (DIM == 3) {
     B2N_CUDA_OK(cudaFuncSetAttribute(k_spread3d<T, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_spread3d<T, NS><<<grid, 256, smem, p.stream>>>(a, p.tab);
+    k_spread3d<T, NS><<<grid, 256, smem, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
   } else {
     B2N_CUDA_OK(cudaFuncSetAttribute(k_spread2d<T, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_spread2d<T, NS><<<grid, 256, smem, p.stream>>>(a, p.tab);
+    k_spread2d<T, NS><<<grid, 256, smem, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
   }
   B2N_LAUNCH_OK();
   return 0;
@@ -87,7 +87,7 @@ int launch_interp_ns(Plan<T> &p, cpx<T> *c, const cpx<T> *postscale, const cpx<T
   auto kern = k_interp<T, NS, DIM>;
   B2N_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)p.pts.sp_cap, (unsigned)ntr);
-  kern<<<grid, 256, smem, p.stream>>>(a, p.tab);
+  kern<<<grid, 256, smem, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   return 0;
 }

@@ -94,16 +94,13 @@ class Plan:
 
     def sort_arrays(self):
         """(idx[M], bin_start[nbins+1]) as torch int32 tensors (copies)."""
-        idx, bs, nb = C.c_void_p(), C.c_void_p(), C.c_int64()
-        ier = self._L.b2n_plan_sort_get(self._h, C.byref(idx), C.byref(bs), C.byref(nb))
-        if ier:
-            raise RuntimeError(f"b2n_plan_sort_get failed with code {ier}")
-        torch.cuda.synchronize()
+        inf = self.info()
+        nb = int(inf.nbins[0]) * int(inf.nbins[1]) * int(inf.nbins[2])
         out_idx = torch.empty(self.M, dtype=torch.int32, device="cuda")
-        out_bs = torch.empty(nb.value + 1, dtype=torch.int32, device="cuda")
-        cudart = torch.cuda.cudart()
-        cudart.cudaMemcpy(out_idx.data_ptr(), idx.value, self.M * 4, 3)
-        cudart.cudaMemcpy(out_bs.data_ptr(), bs.value, (nb.value + 1) * 4, 3)
+        out_bs = torch.empty(nb + 1, dtype=torch.int32, device="cuda")
+        ier = self._L.b2n_plan_sort_copy(self._h, C.c_void_p(out_idx.data_ptr()), C.c_void_p(out_bs.data_ptr()))
+        if ier:
+            raise RuntimeError(f"b2n_plan_sort_copy failed with code {ier}")
         return out_idx, out_bs
 
     def timings(self):

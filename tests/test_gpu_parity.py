@@ -128,7 +128,17 @@ def test_type3_mid_vs_oracle(dim):
     c = (rng.uniform(-1, 1, (2, M)) + 1j * rng.uniform(-1, 1, (2, M))).astype(np.complex64)
     f, info = run_plan(3, dim, (), pts, tgt, c, eps, -1, False, upsampfac=2.0)
     fo = oracle.nufft3(c, [p.astype(np.float64) for p in pts], [s.astype(np.float64) for s in tgt], eps=eps, iflag=-1, prec=1)
-    assert oracle.relerr(f, fo) < 2 * eps + 4e-6   # float type 3: phases at |s x| ~ 130 rad cost ~1e-6 (ops_test.py:120 uses 1e-3)
+    err = oracle.relerr(f, fo)
+    # float type 3: phases reach S*X ~ 43*pi rad per dim, so the fp32 rounding of the rescaled
+    # coordinates costs ~2.5e-7 * S*X*sqrt(dim) whatever the kernel (ops_test.py:120 allows 1e-3)
+    assert err < 2 * eps + 2.5e-7 * 43 * np.pi * np.sqrt(dim)
+    if ref.available():   # ... and the reference library pays the same price on the same inputs
+        r = ref.RefPlan(3, dim, n_trans=2, eps=eps, isign=-1, upsampfac=2.0)
+        r.setpts(*([T(x) for x in pts] + [None] * (3 - dim)), *([T(s) for s in tgt] + [None] * (3 - dim)))
+        fr = r.execute(T(c)).cpu().numpy()
+        r.destroy()
+        assert err < 1.5 * oracle.relerr(fr, fo) + 1e-6
+        assert oracle.relerr(f, fr) < 2 * eps + 2.5e-7 * 43 * np.pi * np.sqrt(dim)
 
 
 def test_binsort_contract_vs_oracle():
