@@ -87,12 +87,16 @@ template <typename T> Plan<T>::~Plan() {
   cudaStream_t st = stream;
   for (int d = 0; d < 3; d++) {
     dev_free(fwker[d], st);
-    dev_free(pts.xs[d], st);
     dev_free(xp[d], st);
     dev_free(sp[d], st);
   }
   dev_free(fw, st);
+  dev_free(pts.rec, st);
+  dev_free(pts.tmp, st);
   dev_free(pts.idx, st);
+  dev_free(pts.key_cnt, st);
+  dev_free(pts.key_start, st);
+  dev_free(pts.bucket_cur, st);
   dev_free(pts.bin_start, st);
   dev_free(pts.sp_off, st);
   dev_free(pts.sp_bin, st);
@@ -162,6 +166,14 @@ int Plan<T>::init(int type_, int dim_, const int64_t *n_modes, int iflag_, int n
     }
   }
   maxsub = opts.gpu_maxsubprobsize > 0 ? opts.gpu_maxsubprobsize : 2048;
+  base_method = method;
+  base_maxsub = maxsub;
+  for (int d = 0; d < 3; d++) base_bin[d] = bin[d];
+  // sliding-window register kernels: 3-D float, ns <= 8, method auto or 3 ("no shared atomics",
+  // the niche of the reference's output-driven method), default bins
+  swr_ok = sizeof(T) == 4 && dim == 3 && ns <= 8 && method == 2 &&
+           (opts.gpu_method == 0 || opts.gpu_method == 3) && opts.gpu_binsizex <= 0 &&
+           opts.gpu_binsizey <= 0 && opts.gpu_binsizez <= 0;
 
   if (type != 3) {
     nmodes = 1;
@@ -231,8 +243,32 @@ int Plan<T>::setpts(int64_t M, const void *x, const void *y, const void *z, int6
   return setpts3(M, (const T *)x, (const T *)y, (const T *)z, N, (const T *)s, (const T *)t, (const T *)u);
 }
 
+// Geometry that depends on the point count: the SWR kernels pay one pass over a 16 x 12 x (ns+1)
+// register window per subproblem, which only amortises on reasonably dense point sets.
+template <typename T> void Plan<T>::set_geometry(int64_t M) {
+  static const char *force = getenv("B2N_FORCE_METHOD");
+  bool swr = swr_ok && nf[0] % 2 == 0 && nf[0] >= 32 && nf[1] >= 32 && nf[2] >= 32 &&
+             (double)M >= 0.08 * (double)nftot;
+  if (force && swr_ok) swr = force[0] == '3';
+  if (swr) {
+    method = 3;
+    swr_bins(ns, bin);
+    maxsub = opts.gpu_maxsubprobsize > 0 ? opts.gpu_maxsubprobsize : 2048;
+  } else {
+    method = base_method;
+    maxsub = base_maxsub;
+    for (int d = 0; d < 3; d++) bin[d] = base_bin[d];
+  }
+  for (int d = 0; d < 3; d++) nbin[d] = d < dim ? cdiv(nf[d], bin[d]) : 1;
+  nbins = (int64_t)nbin[0] * nbin[1] * nbin[2];
+}
+
 template <typename T> int Plan<T>::setpts12(int64_t M, const T *x, const T *y, const T *z) {
   StageTimer tm(opts.debug != 0, stream, &timings[0]);
+  set_geometry(M);
+  if (opts.debug)
+    fprintf(stderr, "[b200nufft] setpts: M=%ld method=%d bins=(%d,%d,%d) maxsub=%d\n", (long)M, method, bin[0],
+            bin[1], bin[2], maxsub);
   return binsort_points<T>(*this, M, x, y, z);
 }
 
@@ -336,6 +372,21 @@ template <typename T> int Plan<T>::execute(void *c, void *fk) {
   return exec3((cpx<T> *)c, (cpx<T> *)fk);
 }
 
+template <typename T>
+int Plan<T>::spread(const cpx<T> *c, const cpx<T> *prescale, cpx<T> *grid, int ntr) {
+  if constexpr (sizeof(T) == 4) {
+    if (method == 3) return spread_swr(*this, c, prescale, grid, ntr);
+  }
+  return method == 2 ? spread_tile<T>(*this, c, prescale, grid, ntr) : spread_gm<T>(*this, c, prescale, grid, ntr);
+}
+template <typename T>
+int Plan<T>::interp(cpx<T> *c, const cpx<T> *postscale, const cpx<T> *grid, int ntr) {
+  if constexpr (sizeof(T) == 4) {
+    if (method == 3) return interp_swr(*this, c, postscale, grid, ntr);
+  }
+  return method == 2 ? interp_tile<T>(*this, c, postscale, grid, ntr) : interp_gm<T>(*this, c, postscale, grid, ntr);
+}
+
 template <typename T> static int run_fft(Plan<T> &p) {
   const int dir = p.iflag >= 0 ? CUFFT_INVERSE : CUFFT_FORWARD;  // cufft_ex(.., iflag): types.h:108-115
   cufftResult r;
@@ -359,9 +410,7 @@ template <typename T> int Plan<T>::exec1(cpx<T> *c, cpx<T> *fk) {
     }
     {
       StageTimer tm(dbg, stream, &timings[1]);
-      int e = method == 2 ? spread_tile<T>(*this, cs, nullptr, grid, blk)
-                          : spread_gm<T>(*this, cs, nullptr, grid, blk);
-      if (e) return e;
+      if (int e = spread(cs, nullptr, grid, blk)) return e;
     }
     if (opts.gpu_spreadinterponly) continue;
     {
@@ -398,9 +447,7 @@ template <typename T> int Plan<T>::exec2(cpx<T> *c, cpx<T> *fk, const cpx<T> *po
     }
     {
       StageTimer tm(dbg, stream, &timings[4]);
-      int e = method == 2 ? interp_tile<T>(*this, cs, postscale, grid, blk)
-                          : interp_gm<T>(*this, cs, postscale, grid, blk);
-      if (e) return e;
+      if (int e = interp(cs, postscale, grid, blk)) return e;
     }
   }
   return 0;
@@ -424,9 +471,7 @@ template <typename T> int Plan<T>::exec3(cpx<T> *c, cpx<T> *fk) {
     }
     {
       StageTimer tm(dbg, stream, &timings[1]);
-      int e = method == 2 ? spread_tile<T>(*this, cs, anyD ? prephase : nullptr, fw, blk)
-                          : spread_gm<T>(*this, cs, anyD ? prephase : nullptr, fw, blk);
-      if (e) return e;
+      if (int e = spread(cs, anyD ? prephase : nullptr, fw, blk)) return e;
     }
     inner->ntransf = blk;
     if (int e = inner->exec2(fks, fw, deconv)) return e;
@@ -452,10 +497,11 @@ template <typename T> void Plan<T>::info(b2n_plan_info *o) {
 
 template <typename T>
 int Plan<T>::sort_get(const int32_t **idx, const int32_t **bin_start, int64_t *nb) {
+  if (int e = materialise_idx<T>(*this)) return e;
   *idx = pts.idx;
   *bin_start = pts.bin_start;
   *nb = nbins;
-  return pts.idx ? 0 : B2N_ERR_PLAN_NOTVALID;
+  return 0;
 }
 
 template struct Plan<float>;

@@ -9,8 +9,7 @@
 namespace b2n {
 
 template <typename T> struct GmArgs {
-  const T *xs, *ys, *zs;
-  const int32_t *idx;
+  const PtRec<T> *rec;
   const cpx<T> *cin;
   cpx<T> *cout;
   const cpx<T> *scale;
@@ -35,22 +34,23 @@ __global__ void __launch_bounds__(128) k_gm(const GmArgs<T> a,
   const int ns = a.ns;
   T k1[MAX_NS], k2[MAX_NS], k3[MAX_NS];
   int s1, s2 = 0, s3 = 0;
+  const PtRec<T> pr = a.rec[p];
   {
-    const T xr = a.xs[p];
+    const T xr = pr.x;
     s1 = window_start(xr, ns);
     eval_kernel_rt<T>(k1, ns, T(s1) - xr, tab);
   }
   if (a.dim > 1) {
-    const T yr = a.ys[p];
+    const T yr = pr.y;
     s2 = window_start(yr, ns);
     eval_kernel_rt<T>(k2, ns, T(s2) - yr, tab);
   }
   if (a.dim > 2) {
-    const T zr = a.zs[p];
+    const T zr = pr.z;
     s3 = window_start(zr, ns);
     eval_kernel_rt<T>(k3, ns, T(s3) - zr, tab);
   }
-  const int j0 = a.idx[p];
+  const int64_t j0 = pr.idx;
   const int n2 = a.dim > 1 ? ns : 1, n3 = a.dim > 2 ? ns : 1;
   cpx<T> *fw = a.fw + (int64_t)blockIdx.y * a.nftot;
   cpx<T> cv;
@@ -93,10 +93,7 @@ static int launch_gm(Plan<T> &p, const cpx<T> *cin, cpx<T> *cout, const cpx<T> *
                      int ntr) {
   if (p.pts.M == 0) return 0;
   GmArgs<T> a;
-  a.xs = p.pts.xs[0];
-  a.ys = p.pts.xs[1];
-  a.zs = p.pts.xs[2];
-  a.idx = p.pts.idx;
+  a.rec = p.pts.rec;
   a.cin = cin;
   a.cout = cout;
   a.scale = scale;

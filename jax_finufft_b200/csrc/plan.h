@@ -9,18 +9,36 @@ namespace b2n {
 
 struct StageTimer;
 
+// One sorted point: folded coordinates + original index, 16 B (float) / 32 B (double), so the
+// spread/interp kernels read a point with one (two) LDG.128 and the sort moves it as a unit.
+template <typename T> struct PtRec;
+template <> struct __align__(16) PtRec<float> {
+  float x, y, z;
+  int32_t idx;
+};
+template <> struct __align__(16) PtRec<double> {
+  double x, y, z;
+  int64_t idx;
+};
+
 // Geometry of one bin-sorted point set (the state cuFINUFFT keeps in idxnupts / binsize /
-// binstartpts / subprob_to_bin -- V/include/cufinufft/types.h:30-101), plus the folded
-// coordinates stored in sorted order so spread/interp read them coalesced.
+// binstartpts / subprob_to_bin -- V/include/cufinufft/types.h:30-101).
 template <typename T> struct PointSet {
   int64_t M = 0;
-  T *xs[3] = {nullptr, nullptr, nullptr};  // fold_rescale'd coords, sorted by bin   [M]
-  int32_t *idx = nullptr;                  // sorted position -> original index      [M]
-  int32_t *bin_start = nullptr;            // exclusive scan of bin histogram        [nbins+1]
-  int32_t *sp_off = nullptr;               // exclusive scan of subproblems per bin  [nbins+1]
-  int32_t *sp_bin = nullptr;               // subproblem -> bin                      [sp_cap]
-  int64_t sp_cap = 0;                      // host-known upper bound on #subproblems
-  int64_t cap_M = 0, cap_bins = 0, cap_sp = 0;
+  PtRec<T> *rec = nullptr;       // points in key order                               [M]
+  PtRec<T> *tmp = nullptr;       // partition scratch (sort pass P1)                  [M]
+  int32_t *idx = nullptr;        // sorted position -> original index; materialised only for
+                                 // b2n_plan_sort_get                                  [M]
+  int32_t *key_cnt = nullptr;    // key histogram, counted down to zero by pass P2    [K]
+  int32_t *key_start = nullptr;  // exclusive scan of the key histogram               [K+1]
+  int32_t *bin_start = nullptr;  // exclusive scan of the BIN histogram               [nbins+1]
+  int32_t *sp_off = nullptr;     // exclusive scan of subproblems per bin             [nbins+1]
+  int32_t *sp_bin = nullptr;     // subproblem -> bin                                 [sp_cap]
+  int32_t *bucket_cur = nullptr; // per-bucket write cursors of pass P1               [256]
+  int64_t sp_cap = 0;            // host-known upper bound on #subproblems
+  int nsub = 1;                  // sub-keys per bin (z cells per bin for the SWR kernels)
+  bool sorted = false;
+  int64_t cap_M = 0, cap_tmp = 0, cap_idx = 0, cap_keys = 0, cap_bins = 0, cap_sp = 0;
 };
 
 struct PlanBase {
@@ -40,7 +58,7 @@ template <typename T> struct Plan : PlanBase {
   int type = 0, dim = 0, iflag = 1, ntransf = 1, batch = 1;
   double eps = 0;
   b2n_opts opts;
-  int method = 0;  // 1 = GM kernels, 2 = tile kernels
+  int method = 0;  // 1 = GM kernels, 2 = tile kernels, 3 = sliding-window register kernels (SWR)
   int ns = 0, ncoef = 0;
   double beta = 0, sigma = 2.0;
   int warn = 0;
@@ -52,6 +70,10 @@ template <typename T> struct Plan : PlanBase {
   int nbin[3] = {1, 1, 1};
   int64_t nbins = 1;
   int maxsub = 1024;
+  // geometry alternatives: the tile/GM choice made at plan time, and whether the sliding-window
+  // register kernels may take over once the point count is known (set_geometry, at setpts)
+  int base_method = 0, base_bin[3] = {1, 1, 1}, base_maxsub = 1024;
+  bool swr_ok = false;
   HornerTable<T> tab;
   cudaStream_t stream = 0;
 
@@ -77,12 +99,15 @@ template <typename T> struct Plan : PlanBase {
   int init(int type, int dim, const int64_t *n_modes, int iflag, int ntransf, double eps,
            const b2n_opts *opts);
   int alloc_grid();
+  void set_geometry(int64_t M);
   int setpts(int64_t M, const void *x, const void *y, const void *z, int64_t N, const void *s,
              const void *t, const void *u) override;
   int setpts12(int64_t M, const T *x, const T *y, const T *z);
   int setpts3(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s, const T *t,
               const T *u);
   int execute(void *c, void *fk) override;
+  int spread(const cpx<T> *c, const cpx<T> *prescale, cpx<T> *grid, int ntr);
+  int interp(cpx<T> *c, const cpx<T> *postscale, const cpx<T> *grid, int ntr);
   int exec1(cpx<T> *c, cpx<T> *fk);
   int exec2(cpx<T> *c, cpx<T> *fk, const cpx<T> *postscale);
   int exec3(cpx<T> *c, cpx<T> *fk);
@@ -95,6 +120,7 @@ template <typename T> struct Plan : PlanBase {
 // ---- stage launchers (one per .cu file) -------------------------------------------------------
 template <typename T>
 int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z);
+template <typename T> int materialise_idx(Plan<T> &p);
 
 // strengths c (gathered through pts.idx, optionally multiplied by prescale[idx]) -> fw (+=)
 template <typename T>
@@ -106,6 +132,11 @@ template <typename T>
 int interp_tile(Plan<T> &p, cpx<T> *c, const cpx<T> *postscale, const cpx<T> *fw, int ntr);
 template <typename T>
 int interp_gm(Plan<T> &p, cpx<T> *c, const cpx<T> *postscale, const cpx<T> *fw, int ntr);
+
+// sliding-window register kernels (swr.cu): 3-D float, ns <= 8, bins from swr_bins()
+void swr_bins(int ns, int *bin);
+int spread_swr(Plan<float> &p, const float2 *c, const float2 *prescale, float2 *fw, int ntr);
+int interp_swr(Plan<float> &p, float2 *c, const float2 *postscale, const float2 *fw, int ntr);
 
 // smem bytes the tile kernels need for (dim, ns, bins); 0 if the combination is unsupported
 template <typename T> size_t tile_smem_bytes(int dim, int ns, const int *bin);

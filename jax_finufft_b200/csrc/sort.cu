@@ -5,14 +5,24 @@
 //
 // Contract kept from the reference: bin id = binx + biny*nbinx + binz*nbinx*nbiny
 // with bin_d = clamp(floor(fold_rescale(x_d)/binsize_d)); bins concatenated by exclusive scan;
-// order inside a bin unspecified.  B200-specific choices: warp-aggregated histogram atomics
-// (one atomic per distinct bin per warp -- clustered inputs no longer serialise on one counter),
-// a device-side scan and subproblem list with NO host readback / stream sync, and the folded
-// coordinates written out in sorted order (12 B/pt once) so the spread/interp kernels stream
-// them coalesced instead of gathering x[idx[i]] (three 32-B sectors per point) every transform.
+// order inside a bin unspecified -- which leaves us free to ORDER the points of a bin by a
+// sub-key (the fine-grid z cell) that the 3-D sliding-window kernels (swr_kernels.cuh) rely on.
 //
-// HBM bytes per point (float, 3-D): pass 1 reads 12, writes 8; pass 2 reads 12+8, writes 16
-// => 56 B/pt algorithmic.
+// B200 design.  The output is an array of 16-byte records {x', y', z', idx} (x' = folded
+// coordinate) in key order, so spread/interp stream one LDG.128 per point.  A single-pass
+// scatter of 1e8 such records writes partial 32-byte sectors all over a 1.6 GB array and was
+// measured at 13.3 GB DRAM read + 12.2 GB write (8x amplification, profiles/r01a_*).  Instead:
+//   P0  k_key_hist    key histogram, warp-aggregated RED.ADD (no per-point output)
+//       scan          key_start[K+1]
+//   P1  k_partition   CTA-local split of a 4096-point chunk into <= 256 buckets of consecutive
+//                     keys; each (CTA, bucket) run is reserved with one atomicAdd and written
+//                     together, so DRAM sees (nearly) full sectors                [skipped when
+//                     the whole record array fits in L2]
+//   P2  k_place       bucket by bucket: pos = key_start[key] + (atomicSub(count[key]) - 1); the
+//                     scattered 16-byte stores of a bucket land in a window of a few MB that
+//                     stays in L2 until its sectors are complete
+// No host readback, no stream sync.  HBM bytes per point (float, 3-D): 12 + (12+16) + (16+16)
+// = 72 B algorithmic.
 #include "plan.h"
 
 namespace b2n {
@@ -133,64 +143,143 @@ struct SortGeom {
   int nf[3];
   int bin[3];
   int nbin[3];
+  int nsub;  // 1, or bin[2]: sub-key = fine-grid z cell inside the bin
 };
 
 template <typename T>
-__device__ __forceinline__ int point_bin(const SortGeom &g, T xr, T yr, T zr) {
+__device__ __forceinline__ int point_key(const SortGeom &g, T xr, T yr, T zr) {
   int b = bin_of(xr, g.bin[0], g.nbin[0]);
   if (g.dim > 1) b += g.nbin[0] * bin_of(yr, g.bin[1], g.nbin[1]);
-  if (g.dim > 2) b += g.nbin[0] * g.nbin[1] * bin_of(zr, g.bin[2], g.nbin[2]);
+  if (g.dim > 2) {
+    const int bz = bin_of(zr, g.bin[2], g.nbin[2]);
+    b += g.nbin[0] * g.nbin[1] * bz;
+    if (g.nsub > 1) {
+      int sub = (int)zr - bz * g.bin[2];
+      sub = sub < 0 ? 0 : (sub >= g.nsub ? g.nsub - 1 : sub);
+      b = b * g.nsub + sub;
+    }
+  }
   return b;
 }
 
-// pass 1: histogram + per-point rank inside its bin (warp-aggregated atomics)
 template <typename T>
-__global__ void __launch_bounds__(256) k_bin_count(SortGeom g, int64_t M, const T *__restrict__ x,
-                                                    const T *__restrict__ y, const T *__restrict__ z,
-                                                    int32_t *__restrict__ hist,
-                                                    int32_t *__restrict__ pbin,
-                                                    int32_t *__restrict__ prank) {
+__device__ __forceinline__ void fold3(const SortGeom &g, int64_t i, const T *__restrict__ x,
+                                      const T *__restrict__ y, const T *__restrict__ z, T &xr, T &yr,
+                                      T &zr) {
+  xr = fold_rescale(x[i], g.nf[0]);
+  yr = g.dim > 1 ? fold_rescale(y[i], g.nf[1]) : T(0);
+  zr = g.dim > 2 ? fold_rescale(z[i], g.nf[2]) : T(0);
+}
+
+template <typename T>
+__device__ __forceinline__ PtRec<T> make_rec(T xr, T yr, T zr, int64_t i) {
+  PtRec<T> r;
+  r.x = xr; r.y = yr; r.z = zr;
+  r.idx = (decltype(r.idx))i;
+  return r;
+}
+
+// P0: key histogram.  One RED per distinct key per warp (clustered inputs do not serialise).
+template <typename T>
+__global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T *__restrict__ x,
+                                                   const T *__restrict__ y, const T *__restrict__ z,
+                                                   int32_t *__restrict__ hist) {
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t Mpad = (M + 31) & ~int64_t(31);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Mpad; i += stride) {
     const bool valid = i < M;
-    int b = -1 - lane;  // unique dummy key for tail lanes
+    int key = -1 - lane;  // unique dummy key for tail lanes
     if (valid) {
-      T xr = fold_rescale(x[i], g.nf[0]);
-      T yr = g.dim > 1 ? fold_rescale(y[i], g.nf[1]) : T(0);
-      T zr = g.dim > 2 ? fold_rescale(z[i], g.nf[2]) : T(0);
-      b = point_bin(g, xr, yr, zr);
+      T xr, yr, zr;
+      fold3(g, i, x, y, z, xr, yr, zr);
+      key = point_key(g, xr, yr, zr);
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, b);
-    const int leader = __ffs(peers) - 1;
-    int base = 0;
-    if (valid && lane == leader) base = atomicAdd(&hist[b], __popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (valid) {
-      pbin[i] = b;
-      prank[i] = base + __popc(peers & ((1u << lane) - 1u));
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[key], __popc(peers));
+  }
+}
+
+// P1: CTA-local partition of a chunk into buckets of consecutive keys (bucket = key >> shift).
+constexpr int PT_T = 256;
+template <typename T> struct PartCfg { static constexpr int E = sizeof(T) == 4 ? 16 : 8; };
+
+template <typename T>
+__global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const T *__restrict__ x,
+                                                     const T *__restrict__ y,
+                                                     const T *__restrict__ z,
+                                                     const int32_t *__restrict__ key_start,
+                                                     int64_t K, int shift, int nbuckets,
+                                                     int32_t *__restrict__ bucket_cur,
+                                                     PtRec<T> *__restrict__ tmp) {
+  constexpr int E = PartCfg<T>::E;
+  __shared__ int cnt[256];
+  __shared__ int base[256];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t c0 = (int64_t)blockIdx.x * (PT_T * E);
+  T xr[E], yr[E], zr[E];
+  int br[E];  // bucket << 16 | rank inside (CTA, bucket)
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    const int64_t i = c0 + e * PT_T + threadIdx.x;
+    br[e] = -1;
+    if (i < M) {
+      fold3(g, i, x, y, z, xr[e], yr[e], zr[e]);
+      const int bkt = point_key(g, xr[e], yr[e], zr[e]) >> shift;
+      br[e] = (bkt << 16) | atomicAdd(&cnt[bkt], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < nbuckets && cnt[threadIdx.x] > 0) {
+    const int64_t k0 = (int64_t)threadIdx.x << shift;
+    base[threadIdx.x] = key_start[k0 < K ? k0 : K] + atomicAdd(&bucket_cur[threadIdx.x], cnt[threadIdx.x]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    if (br[e] >= 0) {
+      const int64_t i = c0 + e * PT_T + threadIdx.x;
+      tmp[base[br[e] >> 16] + (br[e] & 0xffff)] = make_rec<T>(xr[e], yr[e], zr[e], i);
     }
   }
 }
 
-// pass 2: scatter index + folded coordinates to the sorted position
-template <typename T>
-__global__ void __launch_bounds__(256) k_bin_scatter(SortGeom g, int64_t M, const T *__restrict__ x,
-                                                      const T *__restrict__ y,
-                                                      const T *__restrict__ z,
-                                                      const int32_t *__restrict__ bin_start,
-                                                      const int32_t *__restrict__ pbin,
-                                                      const int32_t *__restrict__ prank,
-                                                      int32_t *__restrict__ idx, T *__restrict__ xs,
-                                                      T *__restrict__ ys, T *__restrict__ zs) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
-    const int pos = bin_start[pbin[i]] + prank[i];
-    idx[pos] = (int32_t)i;
-    xs[pos] = fold_rescale(x[i], g.nf[0]);
-    if (g.dim > 1) ys[pos] = fold_rescale(y[i], g.nf[1]);
-    if (g.dim > 2) zs[pos] = fold_rescale(z[i], g.nf[2]);
+// P2: final placement.  RAW: read the caller's arrays (no P1); else read the partitioned records.
+constexpr int PL_E = 8;  // points per thread, consecutive chunks per CTA keep the L2 window small
+template <typename T, bool RAW>
+__global__ void __launch_bounds__(256) k_place(SortGeom g, int64_t M, const T *__restrict__ x,
+                                                const T *__restrict__ y, const T *__restrict__ z,
+                                                const PtRec<T> *__restrict__ tmp,
+                                                const int32_t *__restrict__ key_start,
+                                                int32_t *__restrict__ key_cnt,
+                                                PtRec<T> *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c0 = (int64_t)blockIdx.x * (256 * PL_E);
+#pragma unroll 2
+  for (int e = 0; e < PL_E; e++) {
+    const int64_t i = c0 + e * 256 + threadIdx.x;
+    if (i - lane >= M) break;  // whole warp past the end
+    const bool valid = i < M;
+    PtRec<T> r;
+    int key = -1 - lane;
+    if (valid) {
+      if (RAW) {
+        T xr, yr, zr;
+        fold3(g, i, x, y, z, xr, yr, zr);
+        r = make_rec<T>(xr, yr, zr, i);
+      } else {
+        r = tmp[i];
+      }
+      key = point_key(g, r.x, r.y, r.z);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    const int n = __popc(peers);
+    int b = 0;
+    if (valid && lane == leader) b = atomicSub(&key_cnt[key], n) - n;
+    b = __shfl_sync(0xffffffffu, b, leader);
+    if (valid) out[key_start[key] + b + __popc(peers & ((1u << lane) - 1u))] = r;
   }
 }
 
@@ -198,24 +287,31 @@ __global__ void __launch_bounds__(256) k_bin_scatter(SortGeom g, int64_t M, cons
 template <typename T>
 __global__ void __launch_bounds__(256) k_fold_only(SortGeom g, int64_t M, const T *__restrict__ x,
                                                     const T *__restrict__ y, const T *__restrict__ z,
-                                                    int32_t *__restrict__ idx, T *__restrict__ xs,
-                                                    T *__restrict__ ys, T *__restrict__ zs) {
+                                                    PtRec<T> *__restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
-    idx[i] = (int32_t)i;
-    xs[i] = fold_rescale(x[i], g.nf[0]);
-    if (g.dim > 1) ys[i] = fold_rescale(y[i], g.nf[1]);
-    if (g.dim > 2) zs[i] = fold_rescale(z[i], g.nf[2]);
+    T xr, yr, zr;
+    fold3(g, i, x, y, z, xr, yr, zr);
+    out[i] = make_rec<T>(xr, yr, zr, i);
   }
 }
 
-// subproblems per bin = ceil(count / maxsub)   (precision_independent.cu:75-81)
-__global__ void k_sp_count(int64_t nbins, const int32_t *__restrict__ bin_start, int maxsub,
-                           int32_t *__restrict__ cnt) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_extract_idx(int64_t M, const PtRec<T> *__restrict__ rec,
+                                                      int32_t *__restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) idx[i] = (int32_t)rec[i].idx;
+}
+
+// bin_start[b] = key_start[b * nsub]; subproblems per bin = ceil(count / maxsub)
+// (precision_independent.cu:75-81)
+__global__ void k_sp_count(int64_t nbins, int nsub, const int32_t *__restrict__ key_start,
+                           int maxsub, int32_t *__restrict__ bin_start, int32_t *__restrict__ cnt) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < nbins) {
-    const int n = bin_start[b + 1] - bin_start[b];
-    cnt[b] = (n + maxsub - 1) / maxsub;
+  if (b <= nbins) {
+    const int s = key_start[b * nsub];
+    bin_start[b] = s;
+    if (b < nbins) cnt[b] = (key_start[(b + 1) * nsub] - s + maxsub - 1) / maxsub;
   }
 }
 // subproblem -> bin map   (precision_independent.cu:83-91)
@@ -228,22 +324,22 @@ __global__ void k_sp_fill(int64_t nbins, const int32_t *__restrict__ sp_off,
   }
 }
 
+template <typename U> static int grow(U **p, int64_t *cap, int64_t need, cudaStream_t st) {
+  if (need <= *cap) return 0;
+  dev_free(*p, st);
+  *p = nullptr;
+  *cap = 0;
+  if (int e = dev_alloc_t(p, (size_t)need, st)) return e;
+  *cap = need;
+  return 0;
+}
+
 template <typename T>
 int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   cudaStream_t st = p.stream;
   PointSet<T> &ps = p.pts;
   ps.M = M;
-  // (re)allocate, growing only
-  if (M > ps.cap_M) {
-    for (int d = 0; d < 3; d++) { dev_free(ps.xs[d], st); ps.xs[d] = nullptr; }
-    dev_free(ps.idx, st);
-    ps.idx = nullptr;
-    ps.cap_M = 0;
-    for (int d = 0; d < p.dim; d++)
-      if (int e = dev_alloc_t(&ps.xs[d], (size_t)M, st)) return e;
-    if (int e = dev_alloc_t(&ps.idx, (size_t)M, st)) return e;
-    ps.cap_M = M;
-  }
+  if (int e = grow(&ps.rec, &ps.cap_M, std::max<int64_t>(M, 1), st)) return e;
   SortGeom g;
   g.dim = p.dim;
   for (int d = 0; d < 3; d++) {
@@ -251,15 +347,27 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     g.bin[d] = p.bin[d];
     g.nbin[d] = p.nbin[d];
   }
+  g.nsub = ps.nsub = (p.method == 3 && p.dim == 3) ? p.bin[2] : 1;
   const int nblk = (int)std::min<int64_t>(std::max<int64_t>(cdiv(M, 256), 1), 148 * 16);
-  const bool sorted = p.opts.gpu_sort != 0 || p.method != 1;
-  if (!sorted) {
-    if (M > 0) k_fold_only<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.idx, ps.xs[0], ps.xs[1], ps.xs[2]);  B2N_LAUNCHED(1);
+  ps.sorted = p.opts.gpu_sort != 0 || p.method != 1;
+  if (!ps.sorted) {
+    if (M > 0) k_fold_only<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.rec);  B2N_LAUNCHED(1);
     B2N_LAUNCH_OK();
     ps.sp_cap = 0;
     return 0;
   }
   const int64_t nbins = p.nbins;
+  const int64_t K = nbins * g.nsub;
+  if (K + 1 > 0x7fffffffLL) return B2N_ERR_NDATA_NOTVALID;
+  if (K > ps.cap_keys) {
+    dev_free(ps.key_cnt, st);
+    dev_free(ps.key_start, st);
+    ps.key_cnt = ps.key_start = nullptr;
+    ps.cap_keys = 0;
+    if (int e = dev_alloc_t(&ps.key_cnt, (size_t)K, st)) return e;
+    if (int e = dev_alloc_t(&ps.key_start, (size_t)K + 1, st)) return e;
+    ps.cap_keys = K;
+  }
   if (nbins > ps.cap_bins) {
     dev_free(ps.bin_start, st);
     dev_free(ps.sp_off, st);
@@ -269,42 +377,66 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     if (int e = dev_alloc_t(&ps.sp_off, (size_t)nbins + 1, st)) return e;
     ps.cap_bins = nbins;
   }
+  if (!ps.bucket_cur)
+    if (int e = dev_alloc_t(&ps.bucket_cur, 256, st)) return e;
   const int64_t sp_cap = std::min<int64_t>(nbins, M) + M / p.maxsub + 1;
-  if (sp_cap > ps.cap_sp) {
-    dev_free(ps.sp_bin, st);
-    ps.sp_bin = nullptr;
-    ps.cap_sp = 0;
-    if (int e = dev_alloc_t(&ps.sp_bin, (size_t)sp_cap, st)) return e;
-    ps.cap_sp = sp_cap;
-  }
+  if (int e = grow(&ps.sp_bin, &ps.cap_sp, sp_cap, st)) return e;
   ps.sp_cap = sp_cap;
 
-  int32_t *hist = nullptr, *pbin = nullptr, *prank = nullptr;
-  if (int e = dev_alloc_t(&hist, (size_t)nbins, st)) return e;
-  if (int e = dev_alloc_t(&pbin, (size_t)M, st)) return e;
-  if (int e = dev_alloc_t(&prank, (size_t)M, st)) return e;
-  B2N_CUDA_OK(cudaMemsetAsync(hist, 0, sizeof(int32_t) * nbins, st));
-  if (M > 0) k_bin_count<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, hist, pbin, prank);  B2N_LAUNCHED(1);
+  // P0 + scan
+  B2N_CUDA_OK(cudaMemsetAsync(ps.key_cnt, 0, sizeof(int32_t) * K, st));
+  if (M > 0) k_key_hist<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.key_cnt);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
-  if (int e = exclusive_scan_i32(hist, ps.bin_start, nbins, st)) return e;
-  if (M > 0)
-    k_bin_scatter<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.bin_start, pbin, prank, ps.idx,
-                                           ps.xs[0], ps.xs[1], ps.xs[2]);  B2N_LAUNCHED(1);
-  B2N_LAUNCH_OK();
+  if (int e = exclusive_scan_i32(ps.key_cnt, ps.key_start, K, st)) return e;
+
+  // bucket geometry: windows of ~4 MB of records, at most 256 buckets; one bucket = no P1
+  const int64_t bytes = M * (int64_t)sizeof(PtRec<T>);
+  int64_t want = bytes <= (48LL << 20) ? 1 : std::min<int64_t>(256, (bytes + (4LL << 20) - 1) / (4LL << 20));
+  int shift = 0;
+  while (((K - 1) >> shift) + 1 > want) shift++;
+  const int nbuckets = (int)(((K - 1) >> shift) + 1);
+  if (M > 0) {
+    const int nplace = cdiv(M, 256 * PL_E);
+    if (nbuckets > 1) {
+      if (int e = grow(&ps.tmp, &ps.cap_tmp, M, st)) return e;
+      B2N_CUDA_OK(cudaMemsetAsync(ps.bucket_cur, 0, sizeof(int32_t) * 256, st));
+      k_partition<T><<<cdiv(M, PT_T * PartCfg<T>::E), PT_T, 0, st>>>(g, M, x, y, z, ps.key_start, K, shift,
+                                                                   nbuckets, ps.bucket_cur, ps.tmp);
+      k_place<T, false><<<nplace, 256, 0, st>>>(g, M, x, y, z, ps.tmp, ps.key_start, ps.key_cnt, ps.rec);
+      B2N_LAUNCHED(2);
+    } else {
+      k_place<T, true><<<nplace, 256, 0, st>>>(g, M, x, y, z, nullptr, ps.key_start, ps.key_cnt, ps.rec);
+      B2N_LAUNCHED(1);
+    }
+    B2N_LAUNCH_OK();
+  }
   // subproblem list, entirely on device (the reference reads the total back and syncs,
-  // V/src/cuda/3d/spread3d_wrapper.cu:479-487)
-  const int nb_blk = cdiv(nbins, 256);
-  k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, ps.bin_start, p.maxsub, hist);  B2N_LAUNCHED(1);
-  if (int e = exclusive_scan_i32(hist, ps.sp_off, nbins, st)) return e;
+  // V/src/cuda/3d/spread3d_wrapper.cu:479-487).  key_cnt is all zero again and is reused as
+  // the per-bin subproblem count when it is large enough, else a scratch array is taken.
+  int32_t *spc = nullptr;
+  if (int e = dev_alloc_t(&spc, (size_t)nbins, st)) return e;
+  const int nb_blk = cdiv(nbins + 1, 256);
+  k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, g.nsub, ps.key_start, p.maxsub, ps.bin_start, spc);  B2N_LAUNCHED(1);
+  if (int e = exclusive_scan_i32(spc, ps.sp_off, nbins, st)) return e;
   k_sp_fill<<<nb_blk, 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
-  dev_free(hist, st);
-  dev_free(pbin, st);
-  dev_free(prank, st);
+  dev_free(spc, st);
+  return 0;
+}
+
+// idxnupts for b2n_plan_sort_get: extracted from the records on demand
+template <typename T> int materialise_idx(Plan<T> &p) {
+  PointSet<T> &ps = p.pts;
+  if (!ps.rec) return B2N_ERR_PLAN_NOTVALID;
+  if (int e = grow(&ps.idx, &ps.cap_idx, std::max<int64_t>(ps.M, 1), p.stream)) return e;
+  if (ps.M > 0) k_extract_idx<T><<<cdiv(ps.M, 256), 256, 0, p.stream>>>(ps.M, ps.rec, ps.idx);  B2N_LAUNCHED(1);
+  B2N_LAUNCH_OK();
   return 0;
 }
 
 template int binsort_points<float>(Plan<float> &, int64_t, const float *, const float *, const float *);
 template int binsort_points<double>(Plan<double> &, int64_t, const double *, const double *, const double *);
+template int materialise_idx<float>(Plan<float> &);
+template int materialise_idx<double>(Plan<double> &);
 
 }  // namespace b2n

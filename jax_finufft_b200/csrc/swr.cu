@@ -1,0 +1,79 @@
+// swr.cu -- ns dispatch + launch of the sliding-window register kernels (3-D, float, ns <= 8).
+#include "swr_kernels.cuh"
+
+namespace b2n {
+
+void swr_bins(int ns, int *bin) {
+  bin[0] = 8;
+  bin[1] = 12 - ns;
+  bin[2] = 64;
+}
+
+static void swr_fill(Plan<float> &p, SwrArgs &a) {
+  a.rec = p.pts.rec;
+  a.bin_start = p.pts.bin_start;
+  a.sp_off = p.pts.sp_off;
+  a.sp_bin = p.pts.sp_bin;
+  a.M = p.pts.M;
+  a.nftot = p.nftot;
+  for (int d = 0; d < 3; d++) {
+    a.nf[d] = (int)p.nf[d];
+    a.bin[d] = p.bin[d];
+    a.nbin[d] = p.nbin[d];
+  }
+  a.nbins = p.nbins;
+  a.maxsub = p.maxsub;
+}
+
+template <int NS> struct SwrDispatch {
+  static int spread(Plan<float> &p, const SwrArgs &a, int ntr) {
+    if (p.ns == NS) {
+      using C = SwrCfg<NS>;
+      dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
+      k_swr_spread<NS><<<grid, 32 * C::WARPS, C::smem_bytes(), p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
+      B2N_LAUNCH_OK();
+      return 0;
+    }
+    return SwrDispatch<NS + 1>::spread(p, a, ntr);
+  }
+  static int interp(Plan<float> &p, const SwrArgs &a, int ntr) {
+    if (p.ns == NS) {
+      using C = SwrCfg<NS>;
+      const size_t smem = SwrInterpSmem<NS>::bytes();
+      B2N_CUDA_OK(cudaFuncSetAttribute(k_swr_interp<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
+      k_swr_interp<NS><<<grid, 32 * C::WARPS, smem, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
+      B2N_LAUNCH_OK();
+      return 0;
+    }
+    return SwrDispatch<NS + 1>::interp(p, a, ntr);
+  }
+};
+template <> struct SwrDispatch<9> {
+  static int spread(Plan<float> &, const SwrArgs &, int) { return B2N_ERR_METHOD_NOTVALID; }
+  static int interp(Plan<float> &, const SwrArgs &, int) { return B2N_ERR_METHOD_NOTVALID; }
+};
+
+int spread_swr(Plan<float> &p, const float2 *c, const float2 *prescale, float2 *fw, int ntr) {
+  if (p.pts.M == 0 || p.pts.sp_cap == 0) return 0;
+  SwrArgs a;
+  swr_fill(p, a);
+  a.cin = c;
+  a.cout = nullptr;
+  a.scale = prescale;
+  a.fw = fw;
+  return SwrDispatch<2>::spread(p, a, ntr);
+}
+
+int interp_swr(Plan<float> &p, float2 *c, const float2 *postscale, const float2 *fw, int ntr) {
+  if (p.pts.M == 0 || p.pts.sp_cap == 0) return 0;
+  SwrArgs a;
+  swr_fill(p, a);
+  a.cin = nullptr;
+  a.cout = c;
+  a.scale = postscale;
+  a.fw = const_cast<float2 *>(fw);
+  return SwrDispatch<2>::interp(p, a, ntr);
+}
+
+}  // namespace b2n

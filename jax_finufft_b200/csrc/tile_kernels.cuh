@@ -54,8 +54,7 @@ template <typename T, int NS> struct TileCfg {
 };
 
 template <typename T> struct TileArgs {
-  const T *xs, *ys, *zs;       // folded sorted coords
-  const int32_t *idx;          // sorted -> original
+  const PtRec<T> *rec;         // sorted points: folded coords + original index
   const int32_t *bin_start, *sp_off, *sp_bin;
   const cpx<T> *cin;           // spread: strengths [ntr][M]
   cpx<T> *cout;                // interp: outputs   [ntr][M]
@@ -107,7 +106,7 @@ __device__ __forceinline__ void batch_weights(const TileArgs<T> &a, const Horner
   const int p = p0 + t;
   T ker[NS];
   if (sub == 0) {
-    const T xr = a.xs[p];
+    const T xr = a.rec[p].x;
     const int is = window_start(xr, NS);
     eval_kernel<T, NS>(ker, T(is) - xr, tab);
     const int xl = is - xo + C::HX;
@@ -124,14 +123,14 @@ __device__ __forceinline__ void batch_weights(const TileArgs<T> &a, const Horner
     }
     META[t].x = xa;
   } else if (sub == 1) {
-    const T yr = a.ys[p];
+    const T yr = a.rec[p].y;
     const int is = window_start(yr, NS);
     eval_kernel<T, NS>(ker, T(is) - yr, tab);
 #pragma unroll
     for (int j = 0; j < NS; j++) KY[t * NS + j] = ker[j];
     META[t].y = is - yo + C::H;
   } else if (sub == 2) {
-    const int j0 = a.idx[p];
+    const int j0 = (int)a.rec[p].idx;
     META[t].w = j0;
     cpx<T> cv;
     cv.x = T(1);
@@ -141,7 +140,7 @@ __device__ __forceinline__ void batch_weights(const TileArgs<T> &a, const Horner
       if (a.scale) cv = cmul<T>(cv, a.scale[j0]);
     }
     if (DIM == 3) {
-      const T zr = a.zs[p];
+      const T zr = a.rec[p].z;
       const int is = window_start(zr, NS);
       eval_kernel<T, NS>(ker, T(is) - zr, tab);
       META[t].z = is - zo + C::H;

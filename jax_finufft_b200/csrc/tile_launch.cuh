@@ -34,10 +34,7 @@ template <typename T, int NS, int DIM> struct TileGeom {
 };
 
 template <typename T> inline void fill_args(Plan<T> &p, TileArgs<T> &a) {
-  a.xs = p.pts.xs[0];
-  a.ys = p.pts.xs[1];
-  a.zs = p.pts.xs[2];
-  a.idx = p.pts.idx;
+  a.rec = p.pts.rec;
   a.bin_start = p.pts.bin_start;
   a.sp_off = p.pts.sp_off;
   a.sp_bin = p.pts.sp_bin;
