@@ -704,10 +704,11 @@ void b2n_cache_clear(void) {
   }
 }
 
-int b2n_run(int type, int dim, int is_double, void *stream_, double eps, int iflag, int64_t n_tot,
-            int n_transf, int64_t n_j, const int64_t *n_k, const b2n_opts *opts_in, const void *src,
-            const void *const *pts, const void *const *tgt, void *out) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// The body of b2n_run.  src_ready (optional): an event the stream must wait for before the first
+// execute reads `src` -- lets b2n_run_host overlap the strengths' H2D copy with the bin-sort.
+static int run_core(int type, int dim, int is_double, cudaStream_t stream, double eps, int iflag, int64_t n_tot,
+                    int n_transf, int64_t n_j, const int64_t *n_k, const b2n_opts *opts_in, const void *src,
+                    const void *const *pts, const void *const *tgt, void *out, cudaEvent_t src_ready) {
   b2n_opts o;
   if (opts_in) o = *opts_in; else b2n_default_opts(&o);
   o.gpu_stream = stream;
@@ -756,6 +757,7 @@ int b2n_run(int type, int dim, int is_double, void *stream_, double eps, int ifl
       delete p;
       return ret;
     }
+    if (src_ready && index == 0) cudaStreamWaitEvent(stream, src_ready, 0);
     const char *s_i = (const char *)src + (size_t)index * n_src * n_transf * cs;
     char *o_i = (char *)out + (size_t)index * n_out * n_transf * cs;
     // execute(c, fk): c = nonuniform side, fk = uniform side (or type-3 targets)
@@ -779,6 +781,37 @@ int b2n_run(int type, int dim, int is_double, void *stream_, double eps, int ifl
   return warn;
 }
 
+int b2n_run(int type, int dim, int is_double, void *stream, double eps, int iflag, int64_t n_tot,
+            int n_transf, int64_t n_j, const int64_t *n_k, const b2n_opts *opts, const void *src,
+            const void *const *pts, const void *const *tgt, void *out) {
+  return run_core(type, dim, is_double, (cudaStream_t)stream, eps, iflag, n_tot, n_transf, n_j, n_k, opts, src,
+                  pts, tgt, out, nullptr);
+}
+
+// Host-buffer entry.  Device staging buffers are kept per process (grow-only); the point
+// coordinates go first on a copy stream, the source array follows while the compute stream is
+// already bin-sorting; the result comes back on the compute stream.
+namespace {
+struct HostStage {
+  std::mutex mu;
+  void *buf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // src, out, p0-2, t0-2
+  size_t cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaStream_t copy = nullptr;
+  cudaEvent_t pts_ready = nullptr, src_ready = nullptr, done = nullptr;
+  int device = -1;
+};
+HostStage g_stage;
+int stage_grow(HostStage &h, int i, size_t bytes, cudaStream_t st) {
+  if (bytes <= h.cap[i]) return 0;
+  dev_free(h.buf[i], st);
+  h.buf[i] = nullptr;
+  h.cap[i] = 0;
+  if (int e = dev_alloc(&h.buf[i], bytes, st)) return e;
+  h.cap[i] = bytes;
+  return 0;
+}
+}  // namespace
+
 int b2n_run_host(int type, int dim, int is_double, double eps, int iflag, int64_t n_tot, int n_transf,
                  int64_t n_j, const int64_t *n_k, const b2n_opts *opts, const void *src,
                  const void *const *pts, const void *const *tgt, void *out) {
@@ -792,30 +825,46 @@ int b2n_run_host(int type, int dim, int is_double, double eps, int iflag, int64_
   const size_t src_b = (size_t)n_tot * n_transf * (type == 2 ? n_k_total : n_j) * cs;
   const size_t out_b = (size_t)n_tot * n_transf * (type == 2 ? n_j : n_k_total) * cs;
   const size_t pt_b = (size_t)n_tot * n_j * rs, tg_b = (size_t)n_tot * n_k_total * rs;
-  void *d_src = nullptr, *d_out = nullptr, *d_p[3] = {nullptr, nullptr, nullptr}, *d_t[3] = {nullptr, nullptr, nullptr};
+  HostStage &h = g_stage;
+  std::lock_guard<std::mutex> lk(h.mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B2N_ERR_CUDA_FAILURE;
+  if (h.device != dev) {  // first use, or the caller switched device: drop the old staging area
+    for (int i = 0; i < 8; i++) { if (h.buf[i]) cudaFree(h.buf[i]); h.buf[i] = nullptr; h.cap[i] = 0; }
+    if (h.copy) { cudaStreamDestroy(h.copy); cudaEventDestroy(h.pts_ready); cudaEventDestroy(h.src_ready); cudaEventDestroy(h.done); }
+    B2N_CUDA_OK(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
+    B2N_CUDA_OK(cudaEventCreateWithFlags(&h.pts_ready, cudaEventDisableTiming));
+    B2N_CUDA_OK(cudaEventCreateWithFlags(&h.src_ready, cudaEventDisableTiming));
+    B2N_CUDA_OK(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
+    h.device = dev;
+  }
   int rc = 0;
-  auto cleanup = [&]() {
-    dev_free(d_src, st);
-    dev_free(d_out, st);
-    for (int d = 0; d < 3; d++) { dev_free(d_p[d], st); dev_free(d_t[d], st); }
-  };
-  if ((rc = dev_alloc(&d_src, src_b, st)) || (rc = dev_alloc(&d_out, out_b, st))) { cleanup(); return rc; }
+  if ((rc = stage_grow(h, 0, src_b, st)) || (rc = stage_grow(h, 1, out_b, st))) return rc;
   for (int d = 0; d < dim; d++) {
-    if ((rc = dev_alloc(&d_p[d], pt_b, st))) { cleanup(); return rc; }
-    if (type == 3 && (rc = dev_alloc(&d_t[d], tg_b, st))) { cleanup(); return rc; }
+    if ((rc = stage_grow(h, 2 + d, pt_b, st))) return rc;
+    if (type == 3 && (rc = stage_grow(h, 5 + d, tg_b, st))) return rc;
   }
-  cudaMemcpyAsync(d_src, src, src_b, cudaMemcpyHostToDevice, st);
+  // the copy stream may only start once earlier work on `st` (previous call, allocations) is done
+  B2N_CUDA_OK(cudaEventRecord(h.done, st));
+  B2N_CUDA_OK(cudaStreamWaitEvent(h.copy, h.done, 0));
   for (int d = 0; d < dim; d++) {
-    cudaMemcpyAsync(d_p[d], pts[d], pt_b, cudaMemcpyHostToDevice, st);
-    if (type == 3) cudaMemcpyAsync(d_t[d], tgt[d], tg_b, cudaMemcpyHostToDevice, st);
+    B2N_CUDA_OK(cudaMemcpyAsync(h.buf[2 + d], pts[d], pt_b, cudaMemcpyHostToDevice, h.copy));
+    if (type == 3) B2N_CUDA_OK(cudaMemcpyAsync(h.buf[5 + d], tgt[d], tg_b, cudaMemcpyHostToDevice, h.copy));
   }
-  rc = b2n_run(type, dim, is_double, st, eps, iflag, n_tot, n_transf, n_j, n_k, opts, d_src, d_p,
-               type == 3 ? d_t : nullptr, d_out);
+  B2N_CUDA_OK(cudaEventRecord(h.pts_ready, h.copy));
+  B2N_CUDA_OK(cudaMemcpyAsync(h.buf[0], src, src_b, cudaMemcpyHostToDevice, h.copy));
+  B2N_CUDA_OK(cudaEventRecord(h.src_ready, h.copy));
+  B2N_CUDA_OK(cudaStreamWaitEvent(st, h.pts_ready, 0));
+  void *d_p[3] = {h.buf[2], h.buf[3], h.buf[4]}, *d_t[3] = {h.buf[5], h.buf[6], h.buf[7]};
+  rc = run_core(type, dim, is_double, st, eps, iflag, n_tot, n_transf, n_j, n_k, opts, h.buf[0], d_p,
+                type == 3 ? d_t : nullptr, h.buf[1], h.src_ready);
   if (rc <= 1) {
-    cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(out, h.buf[1], out_b, cudaMemcpyDeviceToHost, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) rc = B2N_ERR_CUDA_FAILURE;
+  } else {
+    cudaStreamSynchronize(h.copy);
+    cudaStreamSynchronize(st);
   }
-  cleanup();
   return rc;
 }
 

@@ -27,7 +27,22 @@
 
 namespace b2n {
 
+// The stream-ordered pool gives memory back to the OS at every synchronisation unless told
+// otherwise; re-mapping gigabytes per call costs far more than the transforms themselves.
+static void keep_pool_memory() {
+  static unsigned long long done = 0;  // bit per device; benign race (idempotent)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64 || (done >> dev) & 1ull) return;
+  cudaMemPool_t mp;
+  if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done |= 1ull << dev;
+}
+
 int dev_alloc(void **p, size_t bytes, cudaStream_t st) {
+  keep_pool_memory();
   if (bytes == 0) bytes = 16;
   cudaError_t e = cudaMallocAsync(p, bytes, st);
   if (e != cudaSuccess) {
