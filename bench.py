@@ -274,12 +274,12 @@ def main_ours(a):
             tf = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tf):
                 traffic = json.load(open(tf)).get(f"{a.workload}:{kern}")
-            line["roofline"] = {"bound": "hbm", "kernel": "k_spread3d<float,7>" if typ == 1 else "k_interp<float,7,3>",
+            line["roofline"] = {"bound": "hbm", "kernel": "k_swr_spread<7>" if typ == 1 else "k_swr_interp<7>",
                                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                 "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel_ms": st[kern],
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                                "note": "3-D ns=7 spread/interp is shared-memory-bound (343 complex cell updates per point), "
-                                        "see DESIGN.md; HBM fraction reported as the contract asks"}
+                                "note": "3-D ns=7 spread/interp is FP32-pipe-bound (343 complex cell updates per point, kept in "
+                                        "registers), see DESIGN.md; HBM fraction reported as the contract asks"}
             line["stages_ms"] = st
         barrier()
 

@@ -23,7 +23,7 @@
 //                     stays in L2 until its sectors are complete
 // No host readback, no stream sync.  HBM bytes per point (float, 3-D): 12 + (12+16) + (16+16)
 // = 72 B algorithmic.
-#include "plan.h"
+#include "swr_kernels.cuh"
 
 namespace b2n {
 
@@ -158,11 +158,25 @@ struct SortGeom {
   int nf[3];
   int bin[3];
   int nbin[3];
-  int nsub;  // 1, or bin[2]: sub-key = fine-grid z cell inside the bin
+  int nsub;    // 1, or bin[2]: sub-key = anchor z cell inside the bin (SWR kernels)
+  int swr_ns;  // 0: reference bins (floor of the folded coordinate); else bins of ANCHOR cells
 };
 
+// SWR geometry (3-D float): bins and sub-key are taken from the anchor cell of the ns-wide window
+// (swr_kernels.cuh).  May shift a coordinate by -nf (periodic image), which is what gets stored.
+__device__ __forceinline__ int swr_key(const SortGeom &g, float &xr, float &yr, float &zr) {
+  const int ux = swr_anchor(xr, g.swr_ns, g.nf[0]);
+  const int uy = swr_anchor(yr, g.swr_ns, g.nf[1]);
+  const int uz = swr_anchor(zr, g.swr_ns, g.nf[2]);
+  const int bz = uz / g.bin[2];
+  const int b = ux / g.bin[0] + g.nbin[0] * (uy / g.bin[1] + g.nbin[1] * bz);
+  return b * g.nsub + (uz - bz * g.bin[2]);
+}
+__device__ __forceinline__ int swr_key(const SortGeom &, double &, double &, double &) { return 0; }
+
 template <typename T>
-__device__ __forceinline__ int point_key(const SortGeom &g, T xr, T yr, T zr) {
+__device__ __forceinline__ int point_key(const SortGeom &g, T &xr, T &yr, T &zr) {
+  if (g.swr_ns) return swr_key(g, xr, yr, zr);
   int b = bin_of(xr, g.bin[0], g.nbin[0]);
   if (g.dim > 1) b += g.nbin[0] * bin_of(yr, g.bin[1], g.nbin[1]);
   if (g.dim > 2) {
@@ -363,6 +377,7 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     g.nbin[d] = p.nbin[d];
   }
   g.nsub = ps.nsub = (p.method == 3 && p.dim == 3) ? p.bin[2] : 1;
+  g.swr_ns = (p.method == 3 && p.dim == 3) ? p.ns : 0;
   const int nblk = (int)std::min<int64_t>(std::max<int64_t>(cdiv(M, 256), 1), 148 * 16);
   ps.sorted = p.opts.gpu_sort != 0 || p.method != 1;
   if (!ps.sorted) {

@@ -3,11 +3,17 @@
 
 namespace b2n {
 
-void swr_bins(int ns, int *bin) {
-  bin[0] = 8;
-  bin[1] = 12 - ns;
-  bin[2] = 64;
+template <int NS> static void swr_bins_ns(int ns, int *bin) {
+  if (ns == NS) {
+    bin[0] = SwrCfg<NS>::BX;
+    bin[1] = SwrCfg<NS>::BY;
+    bin[2] = SwrCfg<NS>::BZ;
+    return;
+  }
+  if constexpr (NS < 8) swr_bins_ns<NS + 1>(ns, bin);
 }
+// bins (in anchor cells) of the sliding-window kernels for kernel width ns
+void swr_bins(int ns, int *bin) { swr_bins_ns<2>(ns, bin); }
 
 static void swr_fill(Plan<float> &p, SwrArgs &a) {
   a.rec = p.pts.rec;
@@ -30,6 +36,7 @@ template <int NS> struct SwrDispatch {
     if (p.ns == NS) {
       using C = SwrCfg<NS>;
       dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
+      B2N_CUDA_OK(cudaFuncSetAttribute(k_swr_spread<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes()));
       k_swr_spread<NS><<<grid, 32 * C::WARPS, C::smem_bytes(), p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
       B2N_LAUNCH_OK();
       return 0;

@@ -133,6 +133,20 @@ def binsort(pts, nf, binsize, prec=0):
     return binid, hist
 
 
+def binsort_anchor(pts, nf, binsize, ns, prec=0):
+    """-> (binid[M], hist[nbins], uz[M]): anchor-cell bins of the 3-D sliding-window kernels."""
+    x, y, z = _pts(pts, 3)
+    M = x.size
+    nb = [(nf[d] + binsize[d] - 1) // binsize[d] for d in range(3)]
+    binid = np.zeros(M, dtype=np.int32)
+    uz = np.zeros(M, dtype=np.int32)
+    hist = np.zeros(nb[0] * nb[1] * nb[2], dtype=np.int32)
+    lib().orc_binsort_anchor(C.c_long(M), _p(x), _p(y), _p(z), C.c_long(nf[0]), C.c_long(nf[1]), C.c_long(nf[2]),
+                             C.c_int(binsize[0]), C.c_int(binsize[1]), C.c_int(binsize[2]), C.c_int(ns),
+                             C.c_int(prec), _p(binid), _p(hist), _p(uz))
+    return binid, hist, uz
+
+
 def spread(pts, c, nf, ns, beta, prec=0):
     """Type-1 gridding of strengths c at pts onto a zeroed fine grid of shape nf[::-1]."""
     dim = len(pts)

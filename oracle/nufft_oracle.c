@@ -248,6 +248,31 @@ void orc_binsort(int dim, long M, const double *x, const double *y, const double
   }
 }
 
+/* Anchor-cell binning used by OUR 3-D sliding-window kernels (jax_finufft_b200/csrc/
+ * swr_kernels.cuh; not a reference function): the bin of a point is taken from the cell
+ * u = window_start(x') + ns/2 (periodic: u == nf -> 0), i.e. from the window of
+ * V/include/cufinufft/utils.h:52-56 (interval) rather than from floor(x').  Also returns the
+ * anchor z cell so that the test can check the in-bin z ordering. */
+void orc_binsort_anchor(long M, const double *x, const double *y, const double *z, long nf1, long nf2,
+                        long nf3, int bx, int by, int bz, int ns, int prec, int32_t *binid,
+                        int32_t *hist, int32_t *uz_out) {
+  int nbx = (int)((nf1 + bx - 1) / bx), nby = (int)((nf2 + by - 1) / by), nbz = (int)((nf3 + bz - 1) / bz);
+  const double *p[3] = {x, y, z};
+  long nf[3] = {nf1, nf2, nf3};
+  memset(hist, 0, sizeof(int32_t) * (size_t)nbx * nby * nbz);
+  for (long i = 0; i < M; i++) {
+    long u[3];
+    for (int d = 0; d < 3; d++) {
+      u[d] = window_start(orc_fold_rescale(p[d][i], nf[d], prec), ns) + ns / 2;
+      if (u[d] >= nf[d]) u[d] -= nf[d];
+    }
+    int b = (int)(u[0] / bx) + nbx * ((int)(u[1] / by) + nby * (int)(u[2] / bz));
+    binid[i] = b;
+    uz_out[i] = (int32_t)u[2];
+    hist[b]++;
+  }
+}
+
 static inline void es_weights(double xr, int ns, double beta, long *start, double *ker) {
   long xs = window_start(xr, ns);
   double x1 = (double)xs - xr;

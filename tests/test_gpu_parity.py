@@ -141,27 +141,42 @@ def test_type3_mid_vs_oracle(dim):
         assert oracle.relerr(f, fr) < 2 * eps + 2.5e-7 * 43 * np.pi * np.sqrt(dim)
 
 
-def test_binsort_contract_vs_oracle():
+@pytest.mark.parametrize("method", [2, 0])
+def test_binsort_contract_vs_oracle(method):
     """SURVEY.md §0.7: histogram, exclusive-scan offsets and per-bin point SETS must match;
-    the order inside a bin is unspecified in the reference (atomicAdd ranks)."""
+    the order inside a bin is unspecified in the reference (atomicAdd ranks).  gpu_method=2 (tile
+    kernels) bins by floor(x') exactly like the reference; the default 3-D float path (sliding-
+    window kernels) bins by the window's anchor cell and orders each bin by anchor z."""
     from jax_finufft_b200.plan import Plan
 
     rng = np.random.default_rng(11)
     M, nm = 300000, (40, 36, 30)
     pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(3)]
     pts[0][:5] = [-np.pi, np.pi, np.nextafter(np.float32(np.pi), np.float32(0)), 0.0, 3 * np.pi]
-    p = Plan(1, nm, eps=1e-6).setpts(*[T(x) for x in pts])
+    pts[1][:5] = pts[0][:5]
+    pts[2][:5] = pts[0][:5]
+    p = Plan(1, nm, eps=1e-6, gpu_method=method).setpts(*[T(x) for x in pts])
     info = p.info()
     idx, bstart = p.sort_arrays()
     idx, bstart = idx.cpu().numpy(), bstart.cpu().numpy()
     p.destroy()
     nf = [int(info.nf[d]) for d in range(3)]
     bins = [int(info.binsize[d]) for d in range(3)]
-    binid, hist = oracle.binsort([x.astype(np.float64) for x in pts], nf, bins, prec=1)
+    p64 = [x.astype(np.float64) for x in pts]
+    if method == 2:
+        assert info.method == 2
+        binid, hist = oracle.binsort(p64, nf, bins, prec=1)
+    else:
+        assert info.method == 3
+        binid, hist, uz = oracle.binsort_anchor(p64, nf, bins, int(info.ns), prec=1)
     assert bstart[0] == 0 and bstart[-1] == M
     assert (np.diff(bstart) == hist).all()                       # histogram + offsets
     assert (np.sort(idx) == np.arange(M)).all()                  # a permutation
     assert (binid[idx] == np.repeat(np.arange(hist.size), hist)).all()   # per-bin sets
+    if method == 0:   # anchor z is non-decreasing inside every bin
+        d = np.diff(uz[idx])
+        same_bin = np.diff(binid[idx]) == 0
+        assert (d[same_bin] >= 0).all()
 
 
 def test_edge_cases_empty_single_far_and_clustered():
