@@ -123,6 +123,32 @@ int b2n_run_host(int type, int dim, int is_double, double eps, int iflag, int64_
                  int n_transf, int64_t n_j, const int64_t *n_k, const b2n_opts *opts,
                  const void *src, const void *const *pts, const void *const *tgt, void *out);
 
+/* ---- the custom-call boundary, flattened to C -------------------------------------------------
+ * One XLA custom call of jax-finufft = one b2n_ffi_call.  `target` is the custom-call target
+ * name the reference registers (lib/jax_finufft_gpu.cc:356-422): "nufft{1,2,3}d{1,2,3}" with a
+ * trailing "f" for single precision.  `attrs` carries the typed FFI attributes in the order of
+ * lib/jax_finufft_gpu.cc:28-60 (src/jax_finufft/lowering.py:157-174); eps is a float attribute
+ * for the ...f targets upstream and is widened here.  `operands` are the device pointers of the
+ * call's arguments in FFI order: source, points x dim, then (type 3) targets x dim -- points
+ * already reversed so that operands[1] is the fastest grid axis (lowering.py:104-105).
+ * `result` is the output buffer.  Returns the FINUFFT code; 0 and 1 map to ffi::Error::Success()
+ * (lib/kernels.cc.cu:52), anything else to ffi::Error::Internal(b2n_strerror(code)). */
+typedef struct b2n_ffi_attrs {
+  double eps;
+  int64_t iflag, n_tot, n_transf, n_j, n_k_1, n_k_2, n_k_3, modeord;
+  double upsampfac;
+  int64_t gpu_method, gpu_sort, gpu_kerevalmeth, gpu_maxbatchsize, debug;
+} b2n_ffi_attrs;
+
+int b2n_ffi_call(const char *target, void *stream, const b2n_ffi_attrs *attrs,
+                 const void *const *operands, int n_operands, void *result);
+/* Number of operands the target takes (1 + dim, or 1 + 2*dim for type 3); -1: unknown target. */
+int b2n_ffi_arity(const char *target);
+/* The 18 target names, NULL-terminated (what registrations() returns as keys). */
+const char *const *b2n_ffi_targets(void);
+/* Message for an error code, in the wording of lib/kernels.cc.cu:54,72,78,88. */
+const char *b2n_strerror(int code);
+
 /* Drop every cached plan / workspace of the calling process (tests, memory pressure). */
 void b2n_cache_clear(void);
 

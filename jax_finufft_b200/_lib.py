@@ -49,11 +49,21 @@ class B2nPlanInfo(C.Structure):
     ]
 
 
+class B2nFfiAttrs(C.Structure):
+    """``b2n_ffi_attrs``: the typed attributes of one custom call (lib/jax_finufft_gpu.cc:28-60)."""
+
+    _fields_ = [("eps", C.c_double)] + [(k, C.c_int64) for k in
+                                        ("iflag", "n_tot", "n_transf", "n_j", "n_k_1", "n_k_2", "n_k_3", "modeord")] + \
+               [("upsampfac", C.c_double)] + [(k, C.c_int64) for k in
+                                              ("gpu_method", "gpu_sort", "gpu_kerevalmeth", "gpu_maxbatchsize", "debug")]
+
+
 EXPORTED = [
     "b2n_default_opts", "b2n_makeplan", "b2n_setpts", "b2n_execute", "b2n_destroy",
     "b2n_plan_info_get", "b2n_plan_sort_get", "b2n_plan_sort_copy", "b2n_run", "b2n_run_host", "b2n_cache_clear",
     "b2n_plan_timings", "b2n_setup_spreader", "b2n_next235beven", "b2n_set_nf_type12",
     "b2n_fseries", "b2n_horner_table", "b2n_default_binsize", "b2n_version", "b2n_launch_count",
+    "b2n_ffi_call", "b2n_ffi_arity", "b2n_ffi_targets", "b2n_strerror",
 ]
 
 
@@ -92,6 +102,11 @@ def lib():
                               C.POINTER(vp), C.POINTER(vp), vp]
         L.b2n_run_host.argtypes = [ci, ci, ci, dbl, ci, i64, ci, i64, C.POINTER(i64), C.POINTER(B2nOpts), vp,
                                    C.POINTER(vp), C.POINTER(vp), vp]
+        L.b2n_ffi_call.argtypes = [C.c_char_p, vp, C.POINTER(B2nFfiAttrs), C.POINTER(vp), ci, vp]
+        L.b2n_ffi_arity.argtypes = [C.c_char_p]
+        L.b2n_ffi_targets.restype = C.POINTER(C.c_char_p)
+        L.b2n_strerror.argtypes = [ci]
+        L.b2n_strerror.restype = C.c_char_p
         L.b2n_cache_clear.restype = None
         L.b2n_setup_spreader.argtypes = [dbl, dbl, ci, ci, C.POINTER(ci), C.POINTER(dbl)]
         L.b2n_next235beven.argtypes = [i64, i64]

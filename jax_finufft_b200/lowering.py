@@ -4,8 +4,8 @@ Upstream, ``lowering()`` (lowering.py:28-178) picks the custom-call target
 ``nufft{dim}d{type}{f}``, packs the FFI attributes, reverses the dimension order (C-order arrays
 -> the backend's x-fastest convention, lowering.py:96-105) and emits the XLA custom call that
 lands in ``run_nufft`` (lib/kernels.cc.cu:25-92).  Here the same attributes are handed straight
-to ``b2n_run`` (include/b200nufft.h), the entry point the XLA-FFI shim
-(csrc/xla_ffi_shim.cc) also calls.  Operands must be CUDA tensors: there is no CPU path.
+to ``b2n_ffi_call`` (include/b200nufft.h) -- the very function the XLA-FFI shim
+(csrc/xla_ffi_shim.cc) calls for each custom call -- which lands in ``b2n_run``.  Operands must be CUDA tensors: there is no CPU path.
 """
 
 import ctypes as C
@@ -15,7 +15,7 @@ import torch
 
 from . import _lib, options
 
-__all__ = ["bind", "op_name", "ffi_attributes"]
+__all__ = ["bind", "op_name", "ffi_attributes", "registrations"]
 
 
 def op_name(ndim, nufft_type, single):
@@ -62,6 +62,17 @@ def ffi_attributes(source_shape, points_shapes, *, output_shape, iflag, eps, opt
     }
 
 
+def registrations():
+    """Target names the extension module exports (``jax_finufft_gpu.registrations()`` keys,
+    lib/jax_finufft_gpu.cc:391-420), read from the library."""
+    tg = _lib.lib().b2n_ffi_targets()
+    names, i = [], 0
+    while tg[i]:
+        names.append(tg[i].decode())
+        i += 1
+    return names
+
+
 def _execute(name, attrs, operands, out):
     """Enqueue one custom call on the current CUDA stream (what the XLA runtime does upstream)."""
     ndim, nufft_type = int(name[5]), int(name[7])
@@ -73,27 +84,17 @@ def _execute(name, attrs, operands, out):
                 f"{t.device}. There is no CPU fallback."
             )
     L = _lib.lib()
-    o = _lib.default_opts()
-    o.modeord = attrs["modeord"]
-    o.upsampfac = attrs["upsampfac"]
-    o.gpu_method = attrs["gpu_method"]
-    o.gpu_sort = attrs["gpu_sort"]
-    o.gpu_kerevalmeth = attrs["gpu_kerevalmeth"]
-    o.gpu_maxbatchsize = attrs["gpu_maxbatchsize"]
-    o.debug = attrs["debug"]
-    n_k = (C.c_int64 * 3)(attrs["n_k_1"], attrs["n_k_2"], attrs["n_k_3"])
-    pts = (C.c_void_p * 3)(*[operands[1 + d].data_ptr() for d in range(ndim)] + [None] * (3 - ndim))
-    if nufft_type == 3:
-        tgt = (C.c_void_p * 3)(*[operands[1 + ndim + d].data_ptr() for d in range(ndim)] + [None] * (3 - ndim))
-    else:
-        tgt = (C.c_void_p * 3)(None, None, None)
+    a = _lib.B2nFfiAttrs()
+    for k, v in attrs.items():
+        setattr(a, k, v)
+    n_ops = 1 + (2 if nufft_type == 3 else 1) * ndim
+    assert len(operands) == n_ops == L.b2n_ffi_arity(name.encode())
+    ops = (C.c_void_p * n_ops)(*[t.data_ptr() for t in operands])
     with torch.cuda.device(out.device):
         stream = torch.cuda.current_stream(out.device).cuda_stream
-        ret = L.b2n_run(nufft_type, ndim, 0 if single else 1, C.c_void_p(stream), attrs["eps"], attrs["iflag"],
-                        attrs["n_tot"], attrs["n_transf"], attrs["n_j"], n_k, C.byref(o),
-                        C.c_void_p(operands[0].data_ptr()), pts, tgt, C.c_void_p(out.data_ptr()))
+        ret = L.b2n_ffi_call(name.encode(), C.c_void_p(stream), C.byref(a), ops, n_ops, C.c_void_p(out.data_ptr()))
     if ret > 1:  # 1 = "eps too small" warning, tolerated (lib/kernels.cc.cu:52)
-        raise RuntimeError(f"b200nufft {name} failed with code {ret}")
+        raise RuntimeError(f"{name}: {L.b2n_strerror(ret).decode()} (code {ret})")
     return out
 
 
