@@ -1,0 +1,95 @@
+"""Multi-GPU paths on real devices (NCCL).  Single-GPU cases run the same code with world = 1;
+the world_size-2 cases need two visible GPUs (gpurun --gpus 2) and are skipped otherwise."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _data(M, nm, seed, dev):
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-np.pi, np.pi, size=(3, M)).astype(np.float32)
+    c = (rng.uniform(-1, 1, M) + 1j * rng.uniform(-1, 1, M)).astype(np.complex64)
+    return [torch.as_tensor(p, device=dev) for p in pts], torch.as_tensor(c, device=dev), pts, c
+
+
+@pytest.mark.parametrize("nm,iflag", [((24, 20, 16), 1), ((16, 18, 30), -1)])
+def test_native_type1_pipeline_single_gpu(nm, iflag):
+    """spread-only plan + slab/pencil FFT + deconvolve == the fused single-GPU nufft1 (<= 2 eps)
+    and the oracle."""
+    import jax_finufft_b200 as J
+    import oracle
+    from jax_finufft_b200 import parallel as P
+
+    dev = torch.device("cuda:0")
+    tp, tc, pts, c = _data(30000, nm, 3, dev)
+    a = P.nufft1_sharded_points(nm, tc, *tp, combine="reduce_scatter", iflag=iflag, eps=1e-6)
+    b = J.nufft1(nm, tc, *tp, iflag=iflag, eps=1e-6)
+    assert a.shape == b.shape == tuple(nm)
+    assert oracle.relerr(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
+    want = oracle.nufft1(tuple(nm[::-1]), c, *pts[::-1].astype(np.float64), iflag=iflag, eps=1e-6, prec=1)
+    assert oracle.relerr(a.cpu().numpy(), want) < 2e-5
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import jax_finufft_b200 as J
+        import oracle
+        from jax_finufft_b200 import parallel as P
+
+        nm, M = (32, 24, 20), 40000
+        tp, tc, pts, c = _data(M, nm, 5, dev)
+        lo, hi = P.shard_range(M, world, rank)
+        loc = [p[lo:hi].contiguous() for p in tp]
+        full = J.nufft1(nm, tc, *tp, eps=1e-6)
+        res = {}
+        a = P.nufft1_sharded_points(nm, tc[lo:hi].contiguous(), *loc, combine="reduce_scatter", eps=1e-6)
+        res["rs"] = oracle.relerr(a.cpu().numpy(), full.cpu().numpy())
+        b = P.nufft1_sharded_points(nm, tc[lo:hi].contiguous(), *loc, combine="psum", eps=1e-6)
+        res["psum"] = oracle.relerr(b.cpu().numpy(), full.cpu().numpy())
+        f = torch.as_tensor((np.random.default_rng(9).uniform(-1, 1, nm) + 0j).astype(np.complex64), device=dev)
+        c2 = P.nufft2_sharded_points(f, *loc, eps=1e-6)
+        c2_full = J.nufft2(f, *tp, eps=1e-6)
+        res["t2"] = oracle.relerr(c2.cpu().numpy(), c2_full[lo:hi].cpu().numpy())
+        stack = torch.stack([tc * (k + 1) for k in range(5)])
+        s = P.nufft1_stacked(nm, stack, *tp, gather=True, eps=1e-6)
+        s_full = J.nufft1(nm, stack, *[p[None] for p in tp], eps=1e-6)
+        res["stack"] = oracle.relerr(s.cpu().numpy(), s_full.cpu().numpy())
+        tg = [torch.as_tensor(np.random.default_rng(11 + d).uniform(-15, 15, 3000).astype(np.float32), device=dev) for d in range(3)]
+        t3 = P.nufft3_sharded_sources(tc[lo:hi].contiguous(), *loc, *tg, eps=1e-6)
+        t3_full = J.nufft3(tc, *tp, *tg, eps=1e-6)
+        res["t3"] = oracle.relerr(t3.cpu().numpy(), t3_full.cpu().numpy())
+        ret[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_world2_nccl_paths_match_single_gpu():
+    world = 2
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        for k, v in ret[r].items():
+            assert v < (1e-5 if k == "t3" else 3e-6), (r, dict(ret[r]))
