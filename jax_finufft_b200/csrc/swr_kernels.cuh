@@ -5,8 +5,7 @@
 // The reference accumulates a subproblem in a shared-memory tile with 2*ns^3 float atomics per
 // point; our tile kernels (tile_kernels.cuh) replaced the atomics by owned LDS/STS read-modify-
 // writes but remain bound by shared-memory wavefronts (~70 per point).  Here the accumulators
-// live in REGISTERS and the FP32 pipe is the binding unit, so the design goal is to waste as few
-// lane-FMAs as possible on cells a point does not touch:
+// live in REGISTERS and instruction issue / the FP32 pipe are the binding units:
 //   * points are binned by the ANCHOR cell u_d = window_start(x_d) + ns/2 (the cell whose
 //     ns-wide stencil the point uses), so all points of an anchor cell touch the same ns cells
 //     per dimension and a bin of b anchor cells touches exactly b + ns - 1 cells;
@@ -15,31 +14,44 @@
 //   * the warp covers the WX x WY = 8 x 12 cells those points can touch: lane (r, q) owns x cell
 //     q (CX = 1; two cells for ns = 8) of rows {r, 4+r, 8+r} ("row slots") and, for each, a ring
 //     of D = ns z planes -- 3 * ns complex accumulators per lane (42 registers at ns = 7);
-//   * points arrive in anchor-z order, so the ring only moves forward: a plane that drops out
-//     of the window is flushed with one red.global.add.v2.f32 per row slot (8 lanes = one 64-byte
-//     row segment, executed in L2) and its registers are zeroed.  Ring slot = plane mod D, so no
-//     register ever moves;
-//   * per batch of 32 points, lane t evaluates the three kernel vectors of point t once and
-//     parks them in (warp-private) shared memory in exactly the form the inner loop consumes:
-//     strength * x-weight as a complex pair per window column, y weights in (row mod 4, row / 4)
-//     order, z weights duplicated (w, w) in ring-slot order;
-//   * per point the warp then issues 6 LDS and, per row slot the point's y window reaches (2.33
-//     of 3 on average), 2 FMUL + ns fma.rn.f32x2 (FFMA2: one instruction per complex cell
-//     update).  Lane efficiency 7/8 (x) * 7/(4 * 2.33) (y) * 7/7 (z) = 66 % at ns = 7.
+//   * points arrive in anchor-z order, so the ring only moves forward: the plane that drops out
+//     of the window is retired with one red.global.add.v2.f32 per row slot (8 lanes = one 64-byte
+//     row segment, executed in L2) and its registers are zeroed;
+//   * STATIC PHASES.  Ring slot of plane p = (p - base) mod D.  The per-subproblem control flow
+//     is a chain of D copies of { consume the points whose window starts at plane cur; retire
+//     plane cur; cur++ }, entered through one switch per batch of 32 points and falling through
+//     from phase to phase, so every accumulator index in the FMA block and in the retire step is
+//     a literal: no select chains, no slot rotation of the z weights.  (The first version kept
+//     one copy of the loop and selected the slot to flush at run time: ~100 executed
+//     instructions per retired plane, 17 % of the kernel -- profiles/r01e_*.)
+//   * per batch of 32 points, lane t evaluates the three kernel vectors of point t once (Horner,
+//     two intervals per FFMA2) and parks them in warp-private shared memory in the form the
+//     inner loop consumes: strength * x-weight as a complex pair per window column, y weights in
+//     (row mod 4, row / 4) order, z weights duplicated (w, w);
+//   * per point the warp then issues 6 LDS, 6 FMUL and 3 * ns FFMA2 (one instruction per complex
+//     cell update), straight-line: row slots a point's y window does not reach multiply by zero
+//     weights instead of branching (a branch per slot costs more issue slots than it saves and
+//     defeats the in-place register allocation of the accumulators).
 // No shared or global atomics with return, no block barriers (warps are independent).
 //
 // Interpolation is the mirror image: the ring holds planes LOADED from the fine grid (64-byte
-// row segments), each point costs (ns + 3) instructions per reachable row slot and one STS; the
-// cross-lane sum is done once per batch through shared memory.
+// row segments, the next plane prefetched one step ahead); the cross-lane sum is done once per
+// group of 8 points through shared memory.
+//
+// FFMA2/FMUL2 are emitted through the sm_100 intrinsics (__ffma2_rn): with inline-asm "+l"
+// operands ptxas routed half of the accumulators through temporaries (20 MOVs per point).
 //
 // Algorithmic HBM bytes: 16 (record) + 8 (strength, 32-B sector gather) per
-// point + one pass over the fine grid.  Binding resource: FP32 pipe (FFMA2 = 2 pipe cycles).
+// point + one pass over the fine grid.
 #pragma once
+#include <type_traits>
+
 #include "plan.h"
 
 namespace b2n {
 
 constexpr int SWR_BZ = 64;  // anchor z cells per bin (subproblems slide along them)
+constexpr int SWR_EMPTY = 0x40000000;
 
 template <int NS> struct SwrCfg {
   static constexpr int D = NS;               // ring depth = z planes an anchor cell's points touch
@@ -52,21 +64,22 @@ template <int NS> struct SwrCfg {
   static constexpr int BY = WY - NS + 1;
   static constexpr int BZ = SWR_BZ;
   static constexpr int PB = 32;              // points per weight batch (one per lane)
+  static constexpr int NP = (NS + 1) / 2;    // Horner interval pairs
   // per-point shared-memory row, in floats
   static constexpr int KXO = 0;              // WX pairs: spread (c.re*kx, c.im*kx); interp (kx, kx)
   static constexpr int KYO = 2 * WX;         // ky[row & 3][row >> 2], 4 x 4
-  static constexpr int KZO = KYO + 16;       // D pairs (kz, kz) in ring-slot order, then META
+  static constexpr int KZO = KYO + 16;       // D pairs (kz, kz), plane order, then META
   static constexpr int KZW = (2 * D + 2 + 3) & ~3;
-  static constexpr int MTO = KZO + KZW - 2;  // META = {first plane of the point's window, row-slot mask}
+  static constexpr int MTO = KZO + KZW - 2;  // META = {first plane of the point's window, unused}
   static constexpr int ROW0 = KZO + KZW;
   // stride/4 odd: lane-strided 16-byte accesses of 8 consecutive lanes hit 8 distinct bank groups
   static constexpr int ROW = (ROW0 / 4) % 2 == 1 ? ROW0 : ROW0 + 4;
   static constexpr int WARPS = 4;
-  static constexpr int OFF = D * 1024;       // makes (plane + OFF) % D non-negative
   static constexpr int MINB = NS <= 5 ? 5 : (NS <= 7 ? 4 : 2);  // CTAs per SM the register budget allows
   static constexpr size_t smem_bytes() { return (size_t)WARPS * PB * ROW * sizeof(float); }
   static_assert(BX >= 1 && BY >= 1, "window too small");
   static_assert(CX == 1 || (BX % 2 == 0 && H % 2 == 0), "paired x cells must stay 16-byte aligned");
+  static_assert(D <= 8, "the phase chain below is written out for D <= 8");
 };
 
 struct SwrArgs {
@@ -82,30 +95,11 @@ struct SwrArgs {
   int maxsub;
 };
 
-__device__ __forceinline__ unsigned long long pack2(float a, float b) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ float2 unpack2(unsigned long long v) {
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
-}
-// acc += a * b, two packed floats at once (sm_100: FFMA2)
-__device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long a, unsigned long long b) {
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
-}
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
+// packed FP32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2, one issue slot for two lanes' worth)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+
 // streaming loads: the records and the strength gather are read once and must not push the
 // fine-grid lines (the REDs' / ring loads' working set) out of L2
 __device__ __forceinline__ float4 ld_stream4(const void *p) {
@@ -141,37 +135,50 @@ __device__ __forceinline__ bool swr_decode(const SwrArgs &a, int sp, int &first,
 }
 
 // ---- phase 1: lane t parks the weights of point p (see SwrCfg for the row layout) ----------------
-template <int NS, bool SPREAD>
+// pr4 = the point record; cv = strength (spread) or (1, 1) (interp: the x row holds (kx, kx))
+template <int NS>
 __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const float4 pr4, float2 cv,
                                             int xa, int ya, float *row) {
-  // pr4 = the point record; cv = strength (spread) or (1, 1) (interp: the x row holds (kx, kx))
   using C = SwrCfg<NS>;
+  constexpr int NP = C::NP;
   const float px = pr4.x, py = pr4.y, pz = pr4.z;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < (C::KYO + 16) / 4; i++) reinterpret_cast<float4 *>(row)[i] = z4;
-  // the three kernel vectors in one Horner sweep (each table coefficient is fetched once)
   const int isx = window_start(px, NS), isy = window_start(py, NS), isz = window_start(pz, NS);
-  float kx[NS], ky[NS], kz[NS];
+  float kx[2 * NP], ky[2 * NP], kz[2 * NP];
   if (!tab.direct) {
+    // the three kernel vectors in one Horner sweep, two intervals per FFMA2; each coefficient
+    // pair is fetched once (warp-uniform constant-bank load).  Column NS of an odd-NS table is 0.
     const float zx = fmaf(2.f, float(isx) - px, float(NS - 1));
     const float zy = fmaf(2.f, float(isy) - py, float(NS - 1));
     const float zz = fmaf(2.f, float(isz) - pz, float(NS - 1));
+    const float2 zx2 = make_float2(zx, zx), zy2 = make_float2(zy, zy), zz2 = make_float2(zz, zz);
+    float2 ax[NP], ay[NP], az[NP];
 #pragma unroll
-    for (int j = 0; j < NS; j++) kx[j] = ky[j] = kz[j] = tab.c[0][j];
+    for (int j = 0; j < NP; j++) ax[j] = ay[j] = az[j] = make_float2(tab.c[0][2 * j], tab.c[0][2 * j + 1]);
     for (int k = 1; k < tab.ncoef; k++) {
 #pragma unroll
-      for (int j = 0; j < NS; j++) {
-        const float cj = tab.c[k][j];
-        kx[j] = fmaf(kx[j], zx, cj);
-        ky[j] = fmaf(ky[j], zy, cj);
-        kz[j] = fmaf(kz[j], zz, cj);
+      for (int j = 0; j < NP; j++) {
+        const float2 cj = make_float2(tab.c[k][2 * j], tab.c[k][2 * j + 1]);
+        ax[j] = fma2(ax[j], zx2, cj);
+        ay[j] = fma2(ay[j], zy2, cj);
+        az[j] = fma2(az[j], zz2, cj);
       }
     }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+      kx[2 * j] = ax[j].x; kx[2 * j + 1] = ax[j].y;
+      ky[2 * j] = ay[j].x; ky[2 * j + 1] = ay[j].y;
+      kz[2 * j] = az[j].x; kz[2 * j + 1] = az[j].y;
+    }
   } else {
-    eval_kernel<float, NS>(kx, float(isx) - px, tab);
-    eval_kernel<float, NS>(ky, float(isy) - py, tab);
-    eval_kernel<float, NS>(kz, float(isz) - pz, tab);
+    float tx[NS], ty[NS], tz[NS];
+    eval_kernel<float, NS>(tx, float(isx) - px, tab);
+    eval_kernel<float, NS>(ty, float(isy) - py, tab);
+    eval_kernel<float, NS>(tz, float(isz) - pz, tab);
+#pragma unroll
+    for (int j = 0; j < NS; j++) { kx[j] = tx[j]; ky[j] = ty[j]; kz[j] = tz[j]; }
   }
   {
     int xl = isx - xa;
@@ -180,7 +187,6 @@ __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const
 #pragma unroll
     for (int j = 0; j < NS; j++) dst[j] = make_float2(cv.x * kx[j], cv.y * kx[j]);
   }
-  int mask;
   {
     int yl = isy - ya;
     yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
@@ -189,35 +195,44 @@ __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const
       const int iy = yl + j;
       row[C::KYO + 4 * (iy & 3) + (iy >> 2)] = ky[j];
     }
-    const int slo = yl >> 2, shi = (yl + NS - 1) >> 2;
-    mask = ((2 << shi) - 1) & ~((1 << slo) - 1);
   }
   {
-    int slot = (isz + C::OFF) % C::D;
-    float2 *dst = reinterpret_cast<float2 *>(row + C::KZO);
+    float *dst = row + C::KZO;
 #pragma unroll
-    for (int j = 0; j < NS; j++) {
-      dst[slot] = make_float2(kz[j], kz[j]);
-      slot = slot + 1 == C::D ? 0 : slot + 1;
-    }
-    *reinterpret_cast<int2 *>(row + C::MTO) = make_int2(isz, mask);
+    for (int j = 0; j + 1 < NS; j += 2)
+      *reinterpret_cast<float4 *>(dst + 2 * j) = make_float4(kz[j], kz[j], kz[j + 1], kz[j + 1]);
+    if constexpr (NS % 2 == 1)
+      *reinterpret_cast<float2 *>(dst + 2 * (NS - 1)) = make_float2(kz[NS - 1], kz[NS - 1]);
+    *reinterpret_cast<int2 *>(row + C::MTO) = make_int2(isz, 0);
   }
 }
 
-// z weights (duplicated pairs, ring-slot order) + META of point row `row`
+// z weights (duplicated pairs, plane order) + first plane of the window of point row `row`
 template <int NS>
-__device__ __forceinline__ void swr_load_kz(const float *row, unsigned long long (&kzp)[SwrCfg<NS>::D],
-                                            int &zw, int &mask) {
+__device__ __forceinline__ void swr_load_kz(const float *row, float2 (&kzp)[SwrCfg<NS>::D], int &zw) {
   using C = SwrCfg<NS>;
   float4 v[C::KZW / 4];
 #pragma unroll
   for (int i = 0; i < C::KZW / 4; i++) v[i] = *reinterpret_cast<const float4 *>(row + C::KZO + 4 * i);
 #pragma unroll
   for (int k = 0; k < C::D; k++)
-    kzp[k] = (k & 1) ? pack2(v[k / 2].z, v[k / 2].w) : pack2(v[k / 2].x, v[k / 2].y);
-  const float4 m = v[C::KZW / 4 - 1];
-  zw = __float_as_int(m.z);
-  mask = __float_as_int(m.w);
+    kzp[k] = (k & 1) ? make_float2(v[k / 2].z, v[k / 2].w) : make_float2(v[k / 2].x, v[k / 2].y);
+  zw = __float_as_int(v[C::KZW / 4 - 1].z);
+}
+
+// this lane's x weight(s) and its three y weights of point row `ro`
+template <int NS>
+__device__ __forceinline__ void swr_load_xy(const float *myx, const float *myy, int ro,
+                                            float2 (&cx)[SwrCfg<NS>::CX], float (&ky)[4]) {
+  if constexpr (SwrCfg<NS>::CX == 1) {
+    cx[0] = *reinterpret_cast<const float2 *>(myx + ro);
+  } else {
+    const float4 v = *reinterpret_cast<const float4 *>(myx + ro);
+    cx[0] = make_float2(v.x, v.y);
+    cx[1] = make_float2(v.z, v.w);
+  }
+  const float4 ky4 = *reinterpret_cast<const float4 *>(myy + ro);
+  ky[0] = ky4.x; ky[1] = ky4.y; ky[2] = ky4.z; ky[3] = ky4.w;
 }
 
 // ==================================================================================== SPREAD
@@ -232,50 +247,59 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
   if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
   float *rows = swr_smem + w * (C::PB * C::ROW);
   const float2 *cin = a.cin + (int64_t)blockIdx.y * a.M;
-  float2 *fw = a.fw + (int64_t)blockIdx.y * a.nftot;
 
   const int r = lane >> 3, q = lane & 7;
   const int xa = x0 - C::H, ya = y0 - C::H;
   const int nf0 = a.nf[0], nf1 = a.nf[1], nf2 = a.nf[2];
-  int rowoff[S];
+  const int64_t pstride = (int64_t)nf0 * nf1;
+  // this lane's cell of each row slot in plane 0
+  float2 *cell[S];
 #pragma unroll
   for (int s = 0; s < S; s++)
-    rowoff[s] = wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0);
-  const int64_t pstride = (int64_t)nf0 * nf1;
+    cell[s] = a.fw + (int64_t)blockIdx.y * a.nftot +
+              (wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0));
 
-  unsigned long long acc[S][CX][D];
+  float2 acc[S][CX][D];
 #pragma unroll
   for (int s = 0; s < S; s++)
 #pragma unroll
     for (int c = 0; c < CX; c++)
 #pragma unroll
-      for (int k = 0; k < D; k++) acc[s][c][k] = 0ull;
+      for (int k = 0; k < D; k++) acc[s][c][k] = make_float2(0.f, 0.f);
 
-  // flush ring slot `slot` (holding plane p) to the fine grid and clear it
-  auto flush = [&](int p, int slot) {
+  // retire plane p held by ring slot K (a literal): RED this lane's cells, clear the slot
+  auto retire = [&](auto kc, int p) {
+    constexpr int K = decltype(kc)::value;
     const int gz = p < 0 ? p + nf2 : (p >= nf2 ? p - nf2 : p);
-    float2 *pl = fw + (int64_t)gz * pstride;
+    const int64_t po = (int64_t)gz * pstride;
 #pragma unroll
-    for (int k = 0; k < D; k++) {
-      if (slot == k) {
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-          if constexpr (CX == 1) {
-            if (acc[s][0][k] & 0x7fffffff7fffffffull) red_add(pl + rowoff[s], unpack2(acc[s][0][k]));
-          } else {
-            if ((acc[s][0][k] | acc[s][1][k]) & 0x7fffffff7fffffffull) {
-              const float2 v0 = unpack2(acc[s][0][k]), v1 = unpack2(acc[s][1][k]);
-              red_add4(reinterpret_cast<float4 *>(pl + rowoff[s]), make_float4(v0.x, v0.y, v1.x, v1.y));
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < CX; c++) acc[s][c][k] = 0ull;
-        }
+    for (int s = 0; s < S; s++) {
+      if constexpr (CX == 1) {
+        red_add(cell[s] + po, acc[s][0][K]);
+      } else {
+        red_add4(reinterpret_cast<float4 *>(cell[s] + po),
+                 make_float4(acc[s][0][K].x, acc[s][0][K].y, acc[s][1][K].x, acc[s][1][K].y));
       }
+#pragma unroll
+      for (int c = 0; c < CX; c++) acc[s][c][K] = make_float2(0.f, 0.f);
     }
   };
+  // all ns^2 x ns cell updates of one point; PH = ring slot of the first plane of its window
+  auto point = [&](auto phc, const float2 *cx, const float *ky, const float2 *kzp) {
+    constexpr int PH = decltype(phc)::value;
+#pragma unroll
+    for (int s = 0; s < S; s++)
+#pragma unroll
+      for (int c = 0; c < CX; c++) {
+        const float2 wv = make_float2(cx[c].x * ky[s], cx[c].y * ky[s]);
+#pragma unroll
+        for (int j = 0; j < D; j++) acc[s][c][(PH + j) % D] = fma2(wv, kzp[j], acc[s][c][(PH + j) % D]);
+      }
+  };
 
-  int cur = 0x40000000;  // first plane held by the ring (sentinel: ring empty)
+  int cur = SWR_EMPTY;  // first plane held by the ring
+  int ph = 0;           // ring slot of plane cur
+  int drain = 0;        // planes still to retire before a jump / the end
   const float *myx = rows + C::KXO + 2 * CX * q;
   const float *myy = rows + C::KYO + 4 * r;
   // Two-deep software pipeline over batches of 32 points: the record of batch b+2 and the
@@ -297,62 +321,67 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
   float2 cA = lane < cnt ? ldc(recA) : make_float2(0.f, 0.f);
   for (int b0 = 0; b0 < cnt; b0 += C::PB) {
     const int nb = min(C::PB, cnt - b0);
+    const bool last = b0 + C::PB >= cnt;
     const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
     const float2 cB = b0 + C::PB + lane < cnt ? ldc(recB) : make_float2(0.f, 0.f);
     __syncwarp();
-    if (lane < nb) swr_weights<NS, true>(tab, recA, cA, xa, ya, rows + lane * C::ROW);
+    if (lane < nb) swr_weights<NS>(tab, recA, cA, xa, ya, rows + lane * C::ROW);
     __syncwarp();
     recA = recB;
     recB = recC;
     cA = cB;
-#pragma unroll 1
-    for (int t = 0; t < nb; t++) {
-      const int ro = t * C::ROW;
-      unsigned long long kzp[D];
-      int zw, mask;
-      swr_load_kz<NS>(rows + ro, kzp, zw, mask);
-      if (zw != cur) {
-        if (cur != 0x40000000) {
-          const int nfl = (zw > cur && zw < cur + D) ? zw - cur : D;  // out of order = full flush
-          int slot = (cur + C::OFF) % D;
-          for (int i = 0; i < nfl; i++) {
-            flush(cur + i, slot);
-            slot = slot + 1 == D ? 0 : slot + 1;
-          }
-        }
-        cur = zw;
-      }
-      float2 cx[CX];
-      if constexpr (CX == 1) {
-        cx[0] = *reinterpret_cast<const float2 *>(myx + ro);
-      } else {
-        const float4 v = *reinterpret_cast<const float4 *>(myx + ro);
-        cx[0] = make_float2(v.x, v.y);
-        cx[1] = make_float2(v.z, v.w);
-      }
-      const float4 ky4 = *reinterpret_cast<const float4 *>(myy + ro);
-      const float ky[4] = {ky4.x, ky4.y, ky4.z, ky4.w};
-      auto do_slot = [&](int s) {
-#pragma unroll
-        for (int c = 0; c < CX; c++) {
-          const unsigned long long wv = pack2(cx[c].x * ky[s], cx[c].y * ky[s]);
-#pragma unroll
-          for (int k = 0; k < D; k++) fma2(acc[s][c][k], wv, kzp[k]);
-        }
-      };
-      // ns >= 5 rows of a 12-row window always reach the middle row slot
-      if (mask & 1) do_slot(0);
-      if (NS >= 5 || (mask & 2)) do_slot(1);
-      if (mask & 4) do_slot(2);
+    int t = 0, ro = 0, zw = 0;
+    if (cur == SWR_EMPTY) cur = __float_as_int(rows[C::MTO]);  // first point: ring empty, ph = 0
+  reenter:
+    for (;;) {
+      switch (ph) {
+#define SWR_SPREAD_PHASE(PH)                                                                    \
+  case PH:                                                                                      \
+    if constexpr (PH < D) {                                                                     \
+      while (t < nb) {                                                                          \
+        float2 kzp[D];                                                                          \
+        swr_load_kz<NS>(rows + ro, kzp, zw);                                                    \
+        if (zw != cur) break;                                                                   \
+        float2 cx[CX];                                                                          \
+        float ky[4];                                                                            \
+        swr_load_xy<NS>(myx, myy, ro, cx, ky);                                                  \
+        point(std::integral_constant<int, PH>{}, cx, ky, kzp);                                  \
+        t++;                                                                                    \
+        ro += C::ROW;                                                                           \
+      }                                                                                         \
+      if (t >= nb && !last) {                                                                   \
+        ph = PH;                                                                                \
+        goto batch_done;                                                                        \
+      }                                                                                         \
+      retire(std::integral_constant<int, PH>{}, cur);                                           \
+      cur++;                                                                                    \
+      if (drain) {                                                                              \
+        if (--drain == 0) {                                                                     \
+          if (t >= nb) goto sub_done;                                                           \
+          cur = zw; /* ring is empty: re-base the phases on the next point's window */          \
+          ph = 0;                                                                               \
+          goto reenter;                                                                         \
+        }                                                                                       \
+      } else if (t >= nb || (unsigned)(zw - cur + 1) >= (unsigned)D) {                          \
+        drain = D - 1; /* end of the subproblem, or a gap wider than the ring */                \
+      }                                                                                         \
     }
-  }
-  if (cur != 0x40000000) {
-    int slot = (cur + C::OFF) % D;
-    for (int i = 0; i < D; i++) {
-      flush(cur + i, slot);
-      slot = slot + 1 == D ? 0 : slot + 1;
+        SWR_SPREAD_PHASE(0)
+        SWR_SPREAD_PHASE(1)
+        SWR_SPREAD_PHASE(2)
+        SWR_SPREAD_PHASE(3)
+        SWR_SPREAD_PHASE(4)
+        SWR_SPREAD_PHASE(5)
+        SWR_SPREAD_PHASE(6)
+        SWR_SPREAD_PHASE(7)
+#undef SWR_SPREAD_PHASE
+        default: break;
+      }
+      ph = 0;
     }
+  batch_done:;
   }
+sub_done:;
 }
 
 // ==================================================================================== INTERP
@@ -374,61 +403,66 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
   int first, cnt, x0, y0;
   if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
   float *rows = swr_smem + w * SwrInterpSmem<NS>::warp_floats;
-  unsigned long long *RES = reinterpret_cast<unsigned long long *>(rows + C::PB * C::ROW);
+  float2 *RES = reinterpret_cast<float2 *>(rows + C::PB * C::ROW);
   float2 *cout = a.cout + (int64_t)blockIdx.y * a.M;
-  const float2 *fw = a.fw + (int64_t)blockIdx.y * a.nftot;
 
   const int r = lane >> 3, q = lane & 7;
   const int xa = x0 - C::H, ya = y0 - C::H;
   const int nf0 = a.nf[0], nf1 = a.nf[1], nf2 = a.nf[2];
-  int rowoff[S];
-#pragma unroll
-  for (int s = 0; s < S; s++)
-    rowoff[s] = wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0);
   const int64_t pstride = (int64_t)nf0 * nf1;
-
-  unsigned long long val[S][CX][D];
+  const float2 *cell[S];  // this lane's cell of each row slot in plane 0
 #pragma unroll
   for (int s = 0; s < S; s++)
-#pragma unroll
-    for (int c = 0; c < CX; c++)
-#pragma unroll
-      for (int k = 0; k < D; k++) val[s][c][k] = 0ull;
+    cell[s] = a.fw + (int64_t)blockIdx.y * a.nftot +
+              (wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0));
 
-  const float2 *ldp[S];  // this lane's cell of each row slot, plane 0
-#pragma unroll
-  for (int s = 0; s < S; s++) ldp[s] = fw + rowoff[s];
-  // fetch this lane's cells of plane p
-  auto fetch = [&](int p, unsigned long long (&v)[S][CX]) {
+  float2 val[S][CX][D];  // ring of loaded planes
+  float2 pre[S][CX];     // plane cur + D, fetched one ring step ahead
+  auto fetch = [&](int p, float2 (&v)[S][CX]) {
     const int gz = p < 0 ? p + nf2 : (p >= nf2 ? p - nf2 : p);
     const int64_t po = (int64_t)gz * pstride;
 #pragma unroll
     for (int s = 0; s < S; s++) {
       if constexpr (CX == 1) {
-        const float2 t = __ldg(ldp[s] + po);
-        v[s][0] = pack2(t.x, t.y);
+        v[s][0] = __ldg(cell[s] + po);
       } else {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(ldp[s] + po));
-        v[s][0] = pack2(t.x, t.y);
-        v[s][1] = pack2(t.z, t.w);
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(cell[s] + po));
+        v[s][0] = make_float2(t.x, t.y);
+        v[s][1] = make_float2(t.z, t.w);
       }
     }
   };
-  auto put = [&](int slot, const unsigned long long (&v)[S][CX]) {
+  // (re)load the whole ring for a window starting at plane p0; phases re-based so that ph = 0
+  auto refill = [&](int p0) {
 #pragma unroll
     for (int k = 0; k < D; k++) {
-      if (slot == k) {
+      float2 v[S][CX];
+      fetch(p0 + k, v);
 #pragma unroll
-        for (int s = 0; s < S; s++)
+      for (int s = 0; s < S; s++)
 #pragma unroll
-          for (int c = 0; c < CX; c++) val[s][c][k] = v[s][c];
-      }
+        for (int c = 0; c < CX; c++) val[s][c][k] = v[s][c];
     }
+    fetch(p0 + D, pre);
   };
-  unsigned long long pre[S][CX];  // plane pre_p, fetched one ring step ahead
-  int pre_p = 0x40000000;
+  // interpolated value (this lane's share) of one point; PH = ring slot of its first plane
+  auto point = [&](auto phc, const float2 *kx, const float *ky, const float2 *kzp) {
+    constexpr int PH = decltype(phc)::value;
+    float2 res = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < S; s++)
+#pragma unroll
+      for (int c = 0; c < CX; c++) {
+        float2 t0 = mul2(val[s][c][PH % D], kzp[0]);
+#pragma unroll
+        for (int j = 1; j < D; j++) t0 = fma2(val[s][c][(PH + j) % D], kzp[j], t0);
+        res = fma2(t0, make_float2(kx[c].x * ky[s], kx[c].y * ky[s]), res);
+      }
+    return res;
+  };
 
-  int cur = 0x40000000;  // first plane held by the ring (sentinel: ring empty)
+  int cur = SWR_EMPTY;  // first plane held by the ring
+  int ph = 0;           // ring slot of plane cur
   const float *myx = rows + C::KXO + 2 * CX * q;
   const float *myy = rows + C::KYO + 4 * r;
   const PtRec<float> *recp = a.rec + first + lane;
@@ -438,78 +472,82 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     const int nb = min(C::PB, cnt - b0);
     const float4 recB = b0 + C::PB + lane < cnt ? ld_stream4(recp + b0 + C::PB) : zrec;
     const int orig = __float_as_int(recA.w);
-    unsigned long long mine = 0ull;  // interpolated value of point b0 + lane
+    float2 mine = make_float2(0.f, 0.f);  // interpolated value of point b0 + lane
     __syncwarp();
-    if (lane < nb) swr_weights<NS, false>(tab, recA, make_float2(1.f, 1.f), xa, ya, rows + lane * C::ROW);
+    if (lane < nb) swr_weights<NS>(tab, recA, make_float2(1.f, 1.f), xa, ya, rows + lane * C::ROW);
     __syncwarp();
     recA = recB;
-#pragma unroll 1
-    for (int t = 0; t < nb; t++) {
-      const int ro = t * C::ROW;
-      unsigned long long kzp[D];
-      int zw, mask;
-      swr_load_kz<NS>(rows + ro, kzp, zw, mask);
-      if (zw != cur) {
-        int pfirst = zw, n = D;
-        if (zw > cur && zw < cur + D) {  // (never true for the empty-ring sentinel)
-          pfirst = cur + D;
-          n = zw - cur;
-        }
-        int slot = (pfirst + C::OFF) % D;
-        for (int i = 0; i < n; i++) {
-          if (pfirst + i == pre_p) {
-            put(slot, pre);
-          } else {
-            unsigned long long v[S][CX];
-            fetch(pfirst + i, v);
-            put(slot, v);
-          }
-          slot = slot + 1 == D ? 0 : slot + 1;
-        }
-        cur = zw;
-        pre_p = zw + D;
-        fetch(pre_p, pre);
-      }
-      float2 kx[CX];  // (kx, kx)
-      if constexpr (CX == 1) {
-        kx[0] = *reinterpret_cast<const float2 *>(myx + ro);
-      } else {
-        const float4 v = *reinterpret_cast<const float4 *>(myx + ro);
-        kx[0] = make_float2(v.x, v.y);
-        kx[1] = make_float2(v.z, v.w);
-      }
-      const float4 ky4 = *reinterpret_cast<const float4 *>(myy + ro);
-      const float ky[4] = {ky4.x, ky4.y, ky4.z, ky4.w};
-      unsigned long long res = 0ull;
-      auto do_slot = [&](int s) {
-#pragma unroll
-        for (int c = 0; c < CX; c++) {
-          unsigned long long t0 = mul2(val[s][c][0], kzp[0]);
-#pragma unroll
-          for (int k = 1; k < D; k++) fma2(t0, val[s][c][k], kzp[k]);
-          fma2(res, t0, pack2(kx[c].x * ky[s], kx[c].y * ky[s]));
-        }
-      };
-      if (mask & 1) do_slot(0);
-      if (NS >= 5 || (mask & 2)) do_slot(1);
-      if (mask & 4) do_slot(2);
-      RES[(t & 7) * 32 + ((lane + t) & 31)] = res;
-      if ((t & 7) == 7 || t == nb - 1) {
-        // group of <= 8 points done: lane j sums quarter j>>3 of row j&7, two butterfly steps
-        // finish the row; point 8g + row lives in lane 8g + row, which keeps the total
-        __syncwarp();
-        const int row8 = lane & 7, part = lane >> 3;
-        unsigned long long s0 = 0ull;
-#pragma unroll
-        for (int j = 0; j < 8; j++) s0 = add2(s0, RES[row8 * 32 + ((part * 8 + j + row8) & 31)]);
-        s0 = add2(s0, __shfl_xor_sync(0xffffffffu, s0, 8));
-        s0 = add2(s0, __shfl_xor_sync(0xffffffffu, s0, 16));
-        if (part == (t >> 3)) mine = s0;
-        __syncwarp();
-      }
+    int t = 0, ro = 0, zw = 0;
+    bool fill = cur == SWR_EMPTY;
+    if (fill) zw = __float_as_int(rows[C::MTO]);
+  reenter:
+    if (fill) {  // first point, or a gap wider than the ring (or disorder): one shared copy
+      cur = zw;
+      refill(cur);
+      ph = 0;
+      fill = false;
     }
+    for (;;) {
+      switch (ph) {
+#define SWR_INTERP_PHASE(PH)                                                                    \
+  case PH:                                                                                      \
+    if constexpr (PH < D) {                                                                     \
+      while (t < nb) {                                                                          \
+        float2 kzp[D];                                                                          \
+        swr_load_kz<NS>(rows + ro, kzp, zw);                                                    \
+        if (zw != cur) break;                                                                   \
+        float2 kx[CX];                                                                          \
+        float ky[4];                                                                            \
+        swr_load_xy<NS>(myx, myy, ro, kx, ky);                                                  \
+        RES[(t & 7) * 32 + ((lane + t) & 31)] = point(std::integral_constant<int, PH>{}, kx, ky, kzp); \
+        if ((t & 7) == 7 || t == nb - 1) {                                                      \
+          /* group of <= 8 points done: lane j sums quarter j>>3 of row j&7, two butterfly */   \
+          /* steps finish the row; point 8g + row lives in lane 8g + row, which keeps it */     \
+          __syncwarp();                                                                         \
+          const int row8 = lane & 7, part = lane >> 3;                                          \
+          float2 s0 = make_float2(0.f, 0.f);                                                    \
+          _Pragma("unroll") for (int j = 0; j < 8; j++)                                         \
+              s0 = add2(s0, RES[row8 * 32 + ((part * 8 + j + row8) & 31)]);                     \
+          s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 8);                                        \
+          s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 8);                                        \
+          s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);                                       \
+          s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);                                       \
+          if (part == (t >> 3)) mine = s0;                                                      \
+          __syncwarp();                                                                         \
+        }                                                                                       \
+        t++;                                                                                    \
+        ro += C::ROW;                                                                           \
+      }                                                                                         \
+      if (t >= nb) {                                                                            \
+        ph = PH;                                                                                \
+        goto batch_done;                                                                        \
+      }                                                                                         \
+      if ((unsigned)(zw - cur) >= (unsigned)D) {                                                \
+        fill = true;                                                                            \
+        goto reenter;                                                                           \
+      }                                                                                         \
+      /* advance one plane: slot PH takes plane cur + D, the next one is requested */           \
+      _Pragma("unroll") for (int s = 0; s < S; s++)                                             \
+          _Pragma("unroll") for (int c = 0; c < CX; c++) val[s][c][PH] = pre[s][c];             \
+      cur++;                                                                                    \
+      fetch(cur + D, pre);                                                                      \
+    }
+        SWR_INTERP_PHASE(0)
+        SWR_INTERP_PHASE(1)
+        SWR_INTERP_PHASE(2)
+        SWR_INTERP_PHASE(3)
+        SWR_INTERP_PHASE(4)
+        SWR_INTERP_PHASE(5)
+        SWR_INTERP_PHASE(6)
+        SWR_INTERP_PHASE(7)
+#undef SWR_INTERP_PHASE
+        default: break;
+      }
+      ph = 0;
+    }
+  batch_done:
     if (lane < nb) {
-      float2 o = unpack2(mine);
+      float2 o = mine;
       if (a.scale) {
         const float2 sc = __ldg(a.scale + orig);
         o = make_float2(o.x * sc.x - o.y * sc.y, o.x * sc.y + o.y * sc.x);
