@@ -207,33 +207,36 @@ __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const
   }
 }
 
-// z weights (duplicated pairs, plane order) + first plane of the window of point row `row`
-template <int NS>
-__device__ __forceinline__ void swr_load_kz(const float *row, float2 (&kzp)[SwrCfg<NS>::D], int &zw) {
+// One point's weights as the inner loop holds them in registers: this lane's x weight(s), its
+// y weights, the (kz, kz) pairs in plane order and the window's first plane (META).  The loops
+// below keep ONE such set live and reload each piece from the NEXT point's row right after its
+// last use ("rolling" loads): every LDS has a whole FMA block to land, a point's row is read
+// exactly once even across phase changes, and no second register set is needed.
+template <int NS> struct SwrRow {
   using C = SwrCfg<NS>;
-  float4 v[C::KZW / 4];
-#pragma unroll
-  for (int i = 0; i < C::KZW / 4; i++) v[i] = *reinterpret_cast<const float4 *>(row + C::KZO + 4 * i);
-#pragma unroll
-  for (int k = 0; k < C::D; k++)
-    kzp[k] = (k & 1) ? make_float2(v[k / 2].z, v[k / 2].w) : make_float2(v[k / 2].x, v[k / 2].y);
-  zw = __float_as_int(v[C::KZW / 4 - 1].z);
-}
-
-// this lane's x weight(s) and its three y weights of point row `ro`
-template <int NS>
-__device__ __forceinline__ void swr_load_xy(const float *myx, const float *myy, int ro,
-                                            float2 (&cx)[SwrCfg<NS>::CX], float (&ky)[4]) {
-  if constexpr (SwrCfg<NS>::CX == 1) {
-    cx[0] = *reinterpret_cast<const float2 *>(myx + ro);
-  } else {
-    const float4 v = *reinterpret_cast<const float4 *>(myx + ro);
-    cx[0] = make_float2(v.x, v.y);
-    cx[1] = make_float2(v.z, v.w);
+  static constexpr int NV = C::KZW / 4;
+  float4 kv[NV];       // kz pairs 2i, 2i+1 (the last one ends with META)
+  float2 cx[C::CX];
+  float4 ky;
+  __device__ __forceinline__ void load_xy(const float *myx, const float *myy, int ro) {
+    if constexpr (C::CX == 1) {
+      cx[0] = *reinterpret_cast<const float2 *>(myx + ro);
+    } else {
+      const float4 v = *reinterpret_cast<const float4 *>(myx + ro);
+      cx[0] = make_float2(v.x, v.y);
+      cx[1] = make_float2(v.z, v.w);
+    }
+    ky = *reinterpret_cast<const float4 *>(myy + ro);
   }
-  const float4 ky4 = *reinterpret_cast<const float4 *>(myy + ro);
-  ky[0] = ky4.x; ky[1] = ky4.y; ky[2] = ky4.z; ky[3] = ky4.w;
-}
+  __device__ __forceinline__ void load_kv(const float *rows, int ro, int i) {
+    kv[i] = *reinterpret_cast<const float4 *>(rows + ro + C::KZO + 4 * i);
+  }
+  __device__ __forceinline__ float2 kz(int j) const {
+    return (j & 1) ? make_float2(kv[j / 2].z, kv[j / 2].w) : make_float2(kv[j / 2].x, kv[j / 2].y);
+  }
+  __device__ __forceinline__ int zw() const { return __float_as_int(kv[NV - 1].z); }
+  __device__ __forceinline__ float kyv(int s) const { return s == 0 ? ky.x : (s == 1 ? ky.y : (s == 2 ? ky.z : ky.w)); }
+};
 
 // ==================================================================================== SPREAD
 template <int NS>
@@ -284,70 +287,90 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
       for (int c = 0; c < CX; c++) acc[s][c][K] = make_float2(0.f, 0.f);
     }
   };
-  // all ns^2 x ns cell updates of one point; PH = ring slot of the first plane of its window
-  auto point = [&](auto phc, const float2 *cx, const float *ky, const float2 *kzp) {
+  // all ns^2 x ns cell updates of the point held in `pr`, then roll `pr` on to the row at `ron`;
+  // PH = ring slot of the first plane of the point's window
+  SwrRow<NS> pr;
+  const float *myx = rows + C::KXO + 2 * CX * q;
+  const float *myy = rows + C::KYO + 4 * r;
+  auto point = [&](auto phc, int ron) {
     constexpr int PH = decltype(phc)::value;
+    float2 wv[S][CX];
 #pragma unroll
     for (int s = 0; s < S; s++)
 #pragma unroll
-      for (int c = 0; c < CX; c++) {
-        const float2 wv = make_float2(cx[c].x * ky[s], cx[c].y * ky[s]);
+      for (int c = 0; c < CX; c++) wv[s][c] = make_float2(pr.cx[c].x * pr.kyv(s), pr.cx[c].y * pr.kyv(s));
+    pr.load_xy(myx, myy, ron);
 #pragma unroll
-        for (int j = 0; j < D; j++) acc[s][c][(PH + j) % D] = fma2(wv, kzp[j], acc[s][c][(PH + j) % D]);
+    for (int i = 0; i < SwrRow<NS>::NV; i++) {
+#pragma unroll
+      for (int j = 2 * i; j < 2 * i + 2; j++) {
+        if (j < D) {
+          const float2 kzj = pr.kz(j);
+#pragma unroll
+          for (int s = 0; s < S; s++)
+#pragma unroll
+            for (int c = 0; c < CX; c++)
+              acc[s][c][(PH + j) % D] = fma2(wv[s][c], kzj, acc[s][c][(PH + j) % D]);
+        }
       }
+      pr.load_kv(rows, ron, i);
+    }
   };
 
   int cur = SWR_EMPTY;  // first plane held by the ring
   int ph = 0;           // ring slot of plane cur
   int drain = 0;        // planes still to retire before a jump / the end
-  const float *myx = rows + C::KXO + 2 * CX * q;
-  const float *myy = rows + C::KYO + 4 * r;
   // Two-deep software pipeline over batches of 32 points: the record of batch b+2 and the
   // strength of batch b+1 (whose address comes from the record of b+1) are in flight while the
   // warp spreads batch b, so neither DRAM round trip is exposed.
   const PtRec<float> *recp = a.rec + first + lane;
   const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto ldc = [&](const float4 &rc) {
+  // strength (and optional per-point factor) of the point of record rc; the complex product is
+  // taken where the value is consumed, one batch later, so that nothing waits on these gathers
+  auto ldc = [&](const float4 &rc, float2 &sc) {
     const int o = __float_as_int(rc.w);
-    float2 cv = ld_stream2(cin + o);
-    if (a.scale) {
-      const float2 sc = __ldg(a.scale + o);
-      cv = make_float2(cv.x * sc.x - cv.y * sc.y, cv.x * sc.y + cv.y * sc.x);
-    }
-    return cv;
+    if (a.scale) sc = __ldg(a.scale + o);
+    return ld_stream2(cin + o);
   };
+  const float2 zero2 = make_float2(0.f, 0.f);
   float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
   float4 recB = lane + C::PB < cnt ? ld_stream4(recp + C::PB) : zrec;
-  float2 cA = lane < cnt ? ldc(recA) : make_float2(0.f, 0.f);
+  float2 sA = make_float2(1.f, 0.f), sB = sA;
+  float2 cA = lane < cnt ? ldc(recA, sA) : zero2;
   for (int b0 = 0; b0 < cnt; b0 += C::PB) {
     const int nb = min(C::PB, cnt - b0);
     const bool last = b0 + C::PB >= cnt;
     const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
-    const float2 cB = b0 + C::PB + lane < cnt ? ldc(recB) : make_float2(0.f, 0.f);
+    const float2 cB = b0 + C::PB + lane < cnt ? ldc(recB, sB) : zero2;
     __syncwarp();
-    if (lane < nb) swr_weights<NS>(tab, recA, cA, xa, ya, rows + lane * C::ROW);
+    if (lane < nb) {
+      float2 cv = cA;
+      if (a.scale) cv = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
+      swr_weights<NS>(tab, recA, cv, xa, ya, rows + lane * C::ROW);
+    }
     __syncwarp();
     recA = recB;
     recB = recC;
     cA = cB;
-    int t = 0, ro = 0, zw = 0;
-    if (cur == SWR_EMPTY) cur = __float_as_int(rows[C::MTO]);  // first point: ring empty, ph = 0
+    sA = sB;
+    int t = 0, ro = 0;
+    pr.load_xy(myx, myy, 0);
+#pragma unroll
+    for (int i = 0; i < SwrRow<NS>::NV; i++) pr.load_kv(rows, 0, i);
+    int zw = pr.zw();
+    if (cur == SWR_EMPTY) cur = zw;  // first point: ring empty, ph = 0
   reenter:
     for (;;) {
       switch (ph) {
 #define SWR_SPREAD_PHASE(PH)                                                                    \
   case PH:                                                                                      \
     if constexpr (PH < D) {                                                                     \
-      while (t < nb) {                                                                          \
-        float2 kzp[D];                                                                          \
-        swr_load_kz<NS>(rows + ro, kzp, zw);                                                    \
-        if (zw != cur) break;                                                                   \
-        float2 cx[CX];                                                                          \
-        float ky[4];                                                                            \
-        swr_load_xy<NS>(myx, myy, ro, cx, ky);                                                  \
-        point(std::integral_constant<int, PH>{}, cx, ky, kzp);                                  \
+      while (t < nb && zw == cur) {                                                             \
+        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
+        point(std::integral_constant<int, PH>{}, ron);                                          \
         t++;                                                                                    \
-        ro += C::ROW;                                                                           \
+        ro = ron;                                                                               \
+        zw = pr.zw();                                                                           \
       }                                                                                         \
       if (t >= nb && !last) {                                                                   \
         ph = PH;                                                                                \
@@ -445,26 +468,47 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     }
     fetch(p0 + D, pre);
   };
-  // interpolated value (this lane's share) of one point; PH = ring slot of its first plane
-  auto point = [&](auto phc, const float2 *kx, const float *ky, const float2 *kzp) {
+  // interpolated value (this lane's share) of the point held in `pr`, then roll `pr` on to the
+  // row at `ron`; PH = ring slot of the first plane of the point's window
+  SwrRow<NS> pr;
+  const float *myx = rows + C::KXO + 2 * CX * q;
+  const float *myy = rows + C::KYO + 4 * r;
+  auto point = [&](auto phc, int ron) {
     constexpr int PH = decltype(phc)::value;
-    float2 res = make_float2(0.f, 0.f);
+    float2 wv[S][CX];
 #pragma unroll
     for (int s = 0; s < S; s++)
 #pragma unroll
-      for (int c = 0; c < CX; c++) {
-        float2 t0 = mul2(val[s][c][PH % D], kzp[0]);
+      for (int c = 0; c < CX; c++) wv[s][c] = make_float2(pr.cx[c].x * pr.kyv(s), pr.cx[c].y * pr.kyv(s));
+    pr.load_xy(myx, myy, ron);
+    float2 part[S][CX];
 #pragma unroll
-        for (int j = 1; j < D; j++) t0 = fma2(val[s][c][(PH + j) % D], kzp[j], t0);
-        res = fma2(t0, make_float2(kx[c].x * ky[s], kx[c].y * ky[s]), res);
+    for (int i = 0; i < SwrRow<NS>::NV; i++) {
+#pragma unroll
+      for (int j = 2 * i; j < 2 * i + 2; j++) {
+        if (j < D) {
+          const float2 kzj = pr.kz(j);
+#pragma unroll
+          for (int s = 0; s < S; s++)
+#pragma unroll
+            for (int c = 0; c < CX; c++)
+              part[s][c] = j == 0 ? mul2(val[s][c][(PH + j) % D], kzj)
+                                  : fma2(val[s][c][(PH + j) % D], kzj, part[s][c]);
+        }
       }
+      pr.load_kv(rows, ron, i);
+    }
+    float2 res = mul2(part[0][0], wv[0][0]);
+#pragma unroll
+    for (int s = 0; s < S; s++)
+#pragma unroll
+      for (int c = 0; c < CX; c++)
+        if (s + c > 0) res = fma2(part[s][c], wv[s][c], res);
     return res;
   };
 
   int cur = SWR_EMPTY;  // first plane held by the ring
   int ph = 0;           // ring slot of plane cur
-  const float *myx = rows + C::KXO + 2 * CX * q;
-  const float *myy = rows + C::KYO + 4 * r;
   const PtRec<float> *recp = a.rec + first + lane;
   const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
@@ -477,9 +521,12 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     if (lane < nb) swr_weights<NS>(tab, recA, make_float2(1.f, 1.f), xa, ya, rows + lane * C::ROW);
     __syncwarp();
     recA = recB;
-    int t = 0, ro = 0, zw = 0;
+    int t = 0, ro = 0;
+    pr.load_xy(myx, myy, 0);
+#pragma unroll
+    for (int i = 0; i < SwrRow<NS>::NV; i++) pr.load_kv(rows, 0, i);
+    int zw = pr.zw();
     bool fill = cur == SWR_EMPTY;
-    if (fill) zw = __float_as_int(rows[C::MTO]);
   reenter:
     if (fill) {  // first point, or a gap wider than the ring (or disorder): one shared copy
       cur = zw;
@@ -492,14 +539,9 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
 #define SWR_INTERP_PHASE(PH)                                                                    \
   case PH:                                                                                      \
     if constexpr (PH < D) {                                                                     \
-      while (t < nb) {                                                                          \
-        float2 kzp[D];                                                                          \
-        swr_load_kz<NS>(rows + ro, kzp, zw);                                                    \
-        if (zw != cur) break;                                                                   \
-        float2 kx[CX];                                                                          \
-        float ky[4];                                                                            \
-        swr_load_xy<NS>(myx, myy, ro, kx, ky);                                                  \
-        RES[(t & 7) * 32 + ((lane + t) & 31)] = point(std::integral_constant<int, PH>{}, kx, ky, kzp); \
+      while (t < nb && zw == cur) {                                                             \
+        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
+        RES[(t & 7) * 32 + ((lane + t) & 31)] = point(std::integral_constant<int, PH>{}, ron);  \
         if ((t & 7) == 7 || t == nb - 1) {                                                      \
           /* group of <= 8 points done: lane j sums quarter j>>3 of row j&7, two butterfly */   \
           /* steps finish the row; point 8g + row lives in lane 8g + row, which keeps it */     \
@@ -516,7 +558,8 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
           __syncwarp();                                                                         \
         }                                                                                       \
         t++;                                                                                    \
-        ro += C::ROW;                                                                           \
+        ro = ron;                                                                               \
+        zw = pr.zw();                                                                           \
       }                                                                                         \
       if (t >= nb) {                                                                            \
         ph = PH;                                                                                \
