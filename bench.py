@@ -152,6 +152,26 @@ def cpu_port_rate(typ, M_full, nm, eps, sample, steps, warmup):
     }
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL (NCCL_DEBUG=VERSION on some boxes) and other
+    native code print to fd 1, so fd 1 is pointed at stderr for the whole run and the JSON line is
+    written to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -168,7 +188,7 @@ def main_reference(a):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -335,13 +355,14 @@ def main_ours(a):
             line["cpu_baseline"] = cpu_port_rate(typ, M, nm, eps, a.cpu_sample, 2, 1)
 
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         main_reference(args)
     else:
