@@ -160,7 +160,14 @@ struct SortGeom {
   int nbin[3];
   int nsub;    // 1, or bin[2]: sub-key = anchor z cell inside the bin (SWR kernels)
   int swr_ns;  // 0: reference bins (floor of the folded coordinate); else bins of ANCHOR cells
+  unsigned magic[3];  // ceil(2^32 / bin[d]) (0 for bin 1): u / bin = umulhi(u, magic), u < 2^26
 };
+
+// u / g.bin[d] without an integer division (the three runtime divides were a third of the
+// instructions of every sort pass): exact for 0 <= u < 2^32 / bin, bin <= 64  =>  u < 2^26
+__device__ __forceinline__ int div_bin(const SortGeom &g, int d, int u) {
+  return g.magic[d] ? (int)__umulhi((unsigned)u, g.magic[d]) : u;
+}
 
 // SWR geometry (3-D float): bins and sub-key are taken from the anchor cell of the ns-wide window
 // (swr_kernels.cuh).  May shift a coordinate by -nf (periodic image), which is what gets stored.
@@ -168,8 +175,8 @@ __device__ __forceinline__ int swr_key(const SortGeom &g, float &xr, float &yr, 
   const int ux = swr_anchor(xr, g.swr_ns, g.nf[0]);
   const int uy = swr_anchor(yr, g.swr_ns, g.nf[1]);
   const int uz = swr_anchor(zr, g.swr_ns, g.nf[2]);
-  const int bz = uz / g.bin[2];
-  const int b = ux / g.bin[0] + g.nbin[0] * (uy / g.bin[1] + g.nbin[1] * bz);
+  const int bz = div_bin(g, 2, uz);
+  const int b = div_bin(g, 0, ux) + g.nbin[0] * (div_bin(g, 1, uy) + g.nbin[1] * bz);
   return b * g.nsub + (uz - bz * g.bin[2]);
 }
 __device__ __forceinline__ int swr_key(const SortGeom &, double &, double &, double &) { return 0; }
@@ -230,32 +237,36 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
 }
 
 // P1: CTA-local partition of a chunk into buckets of consecutive keys (bucket = key >> shift).
+// Phase A ranks every point inside its (CTA, bucket) run with a shared-memory atomic and keeps
+// only {bucket, rank} (one register per point); phase B re-reads the coordinates (the 48 KB chunk
+// is still in L1/L2), folds them again and writes the record.  Holding the folded coordinates
+// across the barrier instead cost 93 registers and two CTAs per SM (profiles/r01d_*).
 constexpr int PT_T = 256;
 template <typename T> struct PartCfg { static constexpr int E = sizeof(T) == 4 ? 16 : 8; };
 
 template <typename T>
-__global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const T *__restrict__ x,
-                                                     const T *__restrict__ y,
-                                                     const T *__restrict__ z,
-                                                     const int32_t *__restrict__ key_start,
-                                                     int64_t K, int shift, int nbuckets,
-                                                     int32_t *__restrict__ bucket_cur,
-                                                     PtRec<T> *__restrict__ tmp) {
+__global__ void __launch_bounds__(PT_T, 4) k_partition(SortGeom g, int64_t M, const T *__restrict__ x,
+                                                        const T *__restrict__ y,
+                                                        const T *__restrict__ z,
+                                                        const int32_t *__restrict__ key_start,
+                                                        int64_t K, int shift, int nbuckets,
+                                                        int32_t *__restrict__ bucket_cur,
+                                                        PtRec<T> *__restrict__ tmp) {
   constexpr int E = PartCfg<T>::E;
   __shared__ int cnt[256];
   __shared__ int base[256];
   cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t c0 = (int64_t)blockIdx.x * (PT_T * E);
-  T xr[E], yr[E], zr[E];
   int br[E];  // bucket << 16 | rank inside (CTA, bucket)
 #pragma unroll
   for (int e = 0; e < E; e++) {
     const int64_t i = c0 + e * PT_T + threadIdx.x;
     br[e] = -1;
     if (i < M) {
-      fold3(g, i, x, y, z, xr[e], yr[e], zr[e]);
-      const int bkt = point_key(g, xr[e], yr[e], zr[e]) >> shift;
+      T xr, yr, zr;
+      fold3(g, i, x, y, z, xr, yr, zr);
+      const int bkt = point_key(g, xr, yr, zr) >> shift;
       br[e] = (bkt << 16) | atomicAdd(&cnt[bkt], 1);
     }
   }
@@ -269,46 +280,64 @@ __global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const
   for (int e = 0; e < E; e++) {
     if (br[e] >= 0) {
       const int64_t i = c0 + e * PT_T + threadIdx.x;
-      tmp[base[br[e] >> 16] + (br[e] & 0xffff)] = make_rec<T>(xr[e], yr[e], zr[e], i);
+      T xr, yr, zr;
+      fold3(g, i, x, y, z, xr, yr, zr);
+      point_key(g, xr, yr, zr);  // applies the periodic shift of the SWR anchor to the coordinates
+      tmp[base[br[e] >> 16] + (br[e] & 0xffff)] = make_rec<T>(xr, yr, zr, i);
     }
   }
 }
 
 // P2: final placement.  RAW: read the caller's arrays (no P1); else read the partitioned records.
-constexpr int PL_E = 8;  // points per thread, consecutive chunks per CTA keep the L2 window small
+// key_start doubles as the write cursor: pos = atomicAdd(&key_start[key], n) (one L2 round trip
+// per distinct key per warp; everything that needs the scan itself -- bin_start, the subproblem
+// list -- is derived BEFORE this pass).  Each thread keeps PL_G points in flight so the atomics'
+// latency overlaps.
+constexpr int PL_G = 4;  // points per thread in flight
+constexpr int PL_E = 8;  // points per thread; consecutive chunks per CTA keep the L2 window small
 template <typename T, bool RAW>
 __global__ void __launch_bounds__(256) k_place(SortGeom g, int64_t M, const T *__restrict__ x,
                                                 const T *__restrict__ y, const T *__restrict__ z,
                                                 const PtRec<T> *__restrict__ tmp,
-                                                const int32_t *__restrict__ key_start,
-                                                int32_t *__restrict__ key_cnt,
+                                                int32_t *__restrict__ key_cursor,
                                                 PtRec<T> *__restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t c0 = (int64_t)blockIdx.x * (256 * PL_E);
-#pragma unroll 2
-  for (int e = 0; e < PL_E; e++) {
-    const int64_t i = c0 + e * 256 + threadIdx.x;
-    if (i - lane >= M) break;  // whole warp past the end
-    const bool valid = i < M;
-    PtRec<T> r;
-    int key = -1 - lane;
-    if (valid) {
-      if (RAW) {
-        T xr, yr, zr;
-        fold3(g, i, x, y, z, xr, yr, zr);
-        r = make_rec<T>(xr, yr, zr, i);
-      } else {
-        r = tmp[i];
+  for (int e0 = 0; e0 < PL_E; e0 += PL_G) {
+    if (c0 + e0 * 256 + (threadIdx.x - lane) >= M) break;  // whole warp past the end
+    PtRec<T> r[PL_G];
+    int key[PL_G], base[PL_G], lr[PL_G];  // lr = leader lane | rank among the peers << 8
+#pragma unroll
+    for (int u = 0; u < PL_G; u++) {
+      const int64_t i = c0 + (e0 + u) * 256 + threadIdx.x;
+      if (i < M) {
+        if (RAW) {
+          T xr, yr, zr;
+          fold3(g, i, x, y, z, xr, yr, zr);
+          r[u] = make_rec<T>(xr, yr, zr, i);
+        } else {
+          r[u] = tmp[i];
+        }
       }
-      key = point_key(g, r.x, r.y, r.z);
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(peers) - 1;
-    const int n = __popc(peers);
-    int b = 0;
-    if (valid && lane == leader) b = atomicSub(&key_cnt[key], n) - n;
-    b = __shfl_sync(0xffffffffu, b, leader);
-    if (valid) out[key_start[key] + b + __popc(peers & ((1u << lane) - 1u))] = r;
+#pragma unroll
+    for (int u = 0; u < PL_G; u++) {
+      const int64_t i = c0 + (e0 + u) * 256 + threadIdx.x;
+      key[u] = i < M ? point_key(g, r[u].x, r[u].y, r[u].z) : -1 - lane;  // dummy keys are unique
+    }
+#pragma unroll
+    for (int u = 0; u < PL_G; u++) {
+      const unsigned peers = __match_any_sync(0xffffffffu, key[u]);
+      const int leader = __ffs(peers) - 1;
+      base[u] = 0;
+      if (key[u] >= 0 && lane == leader) base[u] = atomicAdd(&key_cursor[key[u]], __popc(peers));
+      lr[u] = leader | (__popc(peers & ((1u << lane) - 1u)) << 8);
+    }
+#pragma unroll
+    for (int u = 0; u < PL_G; u++) {
+      const int b = __shfl_sync(0xffffffffu, base[u], lr[u] & 0xff);
+      if (key[u] >= 0) out[b + (lr[u] >> 8)] = r[u];
+    }
   }
 }
 
@@ -376,6 +405,8 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     g.bin[d] = p.bin[d];
     g.nbin[d] = p.nbin[d];
   }
+  for (int d = 0; d < 3; d++)
+    g.magic[d] = g.bin[d] > 1 ? (unsigned)(((1ull << 32) + g.bin[d] - 1) / g.bin[d]) : 0u;
   g.nsub = ps.nsub = (p.method == 3 && p.dim == 3) ? p.bin[2] : 1;
   g.swr_ns = (p.method == 3 && p.dim == 3) ? p.ns : 0;
   const int nblk = (int)std::min<int64_t>(std::max<int64_t>(cdiv(M, 256), 1), 148 * 16);
@@ -419,6 +450,18 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   B2N_LAUNCH_OK();
   if (int e = exclusive_scan_i32(ps.key_cnt, ps.key_start, K, st)) return e;
 
+  // subproblem list, entirely on device (the reference reads the total back and syncs,
+  // V/src/cuda/3d/spread3d_wrapper.cu:479-487).  Derived from the scan BEFORE the placement pass
+  // turns key_start into its write cursors.  key_cnt is free again after the scan and holds the
+  // per-bin subproblem counts.
+  {
+    const int nb_blk = cdiv(nbins + 1, 256);
+    k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, g.nsub, ps.key_start, p.maxsub, ps.bin_start, ps.key_cnt);  B2N_LAUNCHED(1);
+    if (int e = exclusive_scan_i32(ps.key_cnt, ps.sp_off, nbins, st)) return e;
+    k_sp_fill<<<nb_blk, 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);  B2N_LAUNCHED(1);
+    B2N_LAUNCH_OK();
+  }
+
   // bucket geometry: windows of ~4 MB of records, at most 256 buckets; one bucket = no P1
   const int64_t bytes = M * (int64_t)sizeof(PtRec<T>);
   int64_t want = bytes <= (48LL << 20) ? 1 : std::min<int64_t>(256, (bytes + (4LL << 20) - 1) / (4LL << 20));
@@ -432,25 +475,14 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
       B2N_CUDA_OK(cudaMemsetAsync(ps.bucket_cur, 0, sizeof(int32_t) * 256, st));
       k_partition<T><<<cdiv(M, PT_T * PartCfg<T>::E), PT_T, 0, st>>>(g, M, x, y, z, ps.key_start, K, shift,
                                                                    nbuckets, ps.bucket_cur, ps.tmp);
-      k_place<T, false><<<nplace, 256, 0, st>>>(g, M, x, y, z, ps.tmp, ps.key_start, ps.key_cnt, ps.rec);
+      k_place<T, false><<<nplace, 256, 0, st>>>(g, M, x, y, z, ps.tmp, ps.key_start, ps.rec);
       B2N_LAUNCHED(2);
     } else {
-      k_place<T, true><<<nplace, 256, 0, st>>>(g, M, x, y, z, nullptr, ps.key_start, ps.key_cnt, ps.rec);
+      k_place<T, true><<<nplace, 256, 0, st>>>(g, M, x, y, z, nullptr, ps.key_start, ps.rec);
       B2N_LAUNCHED(1);
     }
     B2N_LAUNCH_OK();
   }
-  // subproblem list, entirely on device (the reference reads the total back and syncs,
-  // V/src/cuda/3d/spread3d_wrapper.cu:479-487).  key_cnt is all zero again and is reused as
-  // the per-bin subproblem count when it is large enough, else a scratch array is taken.
-  int32_t *spc = nullptr;
-  if (int e = dev_alloc_t(&spc, (size_t)nbins, st)) return e;
-  const int nb_blk = cdiv(nbins + 1, 256);
-  k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, g.nsub, ps.key_start, p.maxsub, ps.bin_start, spc);  B2N_LAUNCHED(1);
-  if (int e = exclusive_scan_i32(spc, ps.sp_off, nbins, st)) return e;
-  k_sp_fill<<<nb_blk, 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);  B2N_LAUNCHED(1);
-  B2N_LAUNCH_OK();
-  dev_free(spc, st);
   return 0;
 }
 
