@@ -46,6 +46,13 @@ struct PlanBase {
   virtual int setpts(int64_t M, const void *x, const void *y, const void *z, int64_t N,
                      const void *s, const void *t, const void *u) = 0;
   virtual int execute(void *c, void *fk) = 0;
+  // one transform in pieces, for point sets that arrive in chunks (b2n_run_host): PH_BEGIN =
+  // what precedes the non-uniform stage (type 1: clear the fine grid; type 2: amplify + FFT),
+  // PH_BODY = spread / interpolate the CURRENT point set (c = that chunk's strengths / outputs),
+  // PH_END = what follows it (type 1: FFT + deconvolve).  Types 1 and 2, ntransf <= batch.
+  enum { PH_BEGIN = 1, PH_BODY = 2, PH_END = 4 };
+  virtual int exec_phase(int phase, void *c, void *fk) = 0;
+  virtual bool can_chunk(int64_t M, int *nchunk, int64_t *chunk) const = 0;
   virtual void info(b2n_plan_info *out) = 0;
   virtual int sort_get(const int32_t **idx, const int32_t **bin_start, int64_t *nbins) = 0;
   virtual void set_stream(cudaStream_t s) = 0;
@@ -106,6 +113,8 @@ template <typename T> struct Plan : PlanBase {
   int setpts3(int64_t M, const T *x, const T *y, const T *z, int64_t N, const T *s, const T *t,
               const T *u);
   int execute(void *c, void *fk) override;
+  int exec_phase(int phase, void *c, void *fk) override;
+  bool can_chunk(int64_t M, int *nchunk, int64_t *chunk) const override;
   int spread(const cpx<T> *c, const cpx<T> *prescale, cpx<T> *grid, int ntr);
   int interp(cpx<T> *c, const cpx<T> *postscale, const cpx<T> *grid, int ntr);
   int exec1(cpx<T> *c, cpx<T> *fk);
