@@ -350,6 +350,28 @@ def main_ours(a):
             torch.cuda.empty_cache()
         line["also"] = also
 
+        # ---- N > 1: the one path with a real exchange step: ONE 3-D type 1 with its
+        # M points split across the ranks by index range (strong scaling of a single transform).
+        # reduce_scatter = native path (private fine grids summed by NCCL reduce-scatter over
+        # NVLink, slab/pencil FFT divided by N); psum = what jax-finufft gets from shard_map
+        # (every rank runs the full FFT, all-reduce of the output modes).
+        if world > 1 and a.workload == "c3_t1":
+            from jax_finufft_b200 import parallel as P
+            Ml = M // world
+            w = workload("c3_t1")
+            lp = [p_[:Ml].clone() for p_ in w[5]]
+            lc = w[6][:Ml].clone()
+            del w
+            torch.cuda.empty_cache()
+            sharded = {}
+            for mode in ("reduce_scatter", "psum"):
+                fn = lambda: P.nufft1_sharded_points(nm, lc, *lp, combine=mode, gather=False, eps=eps, iflag=1)
+                ms_s, _ = timed(fn, 3, 2)
+                sharded[mode] = {"value": world * Ml / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s,
+                                 "M_total": world * Ml, "scaling": "strong"}
+            line["also"]["c3_t1_points_sharded"] = sharded
+            del lp, lc
+
         # ---- CPU baseline: the oracle port on the host cores (rank 0, N=1 only)
         if rank == 0 and world == 1:
             line["cpu_baseline"] = cpu_port_rate(typ, M, nm, eps, a.cpu_sample, 2, 1)

@@ -237,53 +237,86 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
 }
 
 // P1: CTA-local partition of a chunk into buckets of consecutive keys (bucket = key >> shift).
-// Phase A ranks every point inside its (CTA, bucket) run with a shared-memory atomic and keeps
-// only {bucket, rank} (one register per point); phase B re-reads the coordinates (the 48 KB chunk
-// is still in L1/L2), folds them again and writes the record.  Holding the folded coordinates
-// across the barrier instead cost 93 registers and two CTAs per SM (profiles/r01d_*).
+// The chunk's records are staged in shared memory and leave it in bucket order, so that every
+// warp store covers a few contiguous runs (full 32-byte sectors, a handful of L2 requests)
+// instead of 32 scattered half-sectors.  The first version wrote each record straight to
+// tmp[base[bucket] + rank]: 1e8 partial-sector L2 requests, 2.1 ms at C3 (profiles/r01e_sort_*);
+// all three sort passes were bound by the rate of such scattered L2 requests, not by DRAM.
+//   A  fold, key, rank inside (CTA, bucket) by shared-memory atomic; record -> smem slot
+//   B  exclusive scan of the 256 bucket counts; one global atomicAdd per non-empty bucket
+//      reserves the CTA's run in that bucket
+//   C  dest = off[bucket] + rank: perm[dest] = slot, pbkt[dest] = bucket
+//   D  thread t writes output positions t, t + T, ...: tmp[base[b] + j - off[b]] = smem[perm[j]]
 constexpr int PT_T = 256;
-template <typename T> struct PartCfg { static constexpr int E = sizeof(T) == 4 ? 16 : 8; };
+template <typename T> struct PartCfg { static constexpr int E = sizeof(T) == 4 ? 8 : 4; };
 
 template <typename T>
-__global__ void __launch_bounds__(PT_T, 4) k_partition(SortGeom g, int64_t M, const T *__restrict__ x,
-                                                        const T *__restrict__ y,
-                                                        const T *__restrict__ z,
-                                                        const int32_t *__restrict__ key_start,
-                                                        int64_t K, int shift, int nbuckets,
-                                                        int32_t *__restrict__ bucket_cur,
-                                                        PtRec<T> *__restrict__ tmp) {
-  constexpr int E = PartCfg<T>::E;
-  __shared__ int cnt[256];
-  __shared__ int base[256];
+__global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const T *__restrict__ x,
+                                                     const T *__restrict__ y,
+                                                     const T *__restrict__ z,
+                                                     const int32_t *__restrict__ key_start,
+                                                     int64_t K, int shift, int nbuckets,
+                                                     int32_t *__restrict__ bucket_cur,
+                                                     PtRec<T> *__restrict__ tmp) {
+  constexpr int E = PartCfg<T>::E, N = PT_T * E;
+  __shared__ PtRec<T> srec[N];
+  __shared__ unsigned short perm[N];
+  __shared__ unsigned char pbkt[N];
+  __shared__ int cnt[256], off[256], base[256], wsum[PT_T / 32];
   cnt[threadIdx.x] = 0;
   __syncthreads();
-  const int64_t c0 = (int64_t)blockIdx.x * (PT_T * E);
+  const int64_t c0 = (int64_t)blockIdx.x * N;
+  const int nloc = (int)min((int64_t)N, M - c0);
   int br[E];  // bucket << 16 | rank inside (CTA, bucket)
 #pragma unroll
   for (int e = 0; e < E; e++) {
-    const int64_t i = c0 + e * PT_T + threadIdx.x;
+    const int sl = e * PT_T + threadIdx.x;
     br[e] = -1;
-    if (i < M) {
+    if (sl < nloc) {
       T xr, yr, zr;
-      fold3(g, i, x, y, z, xr, yr, zr);
+      fold3(g, c0 + sl, x, y, z, xr, yr, zr);
       const int bkt = point_key(g, xr, yr, zr) >> shift;
       br[e] = (bkt << 16) | atomicAdd(&cnt[bkt], 1);
+      srec[sl] = make_rec<T>(xr, yr, zr, c0 + sl);
     }
   }
   __syncthreads();
-  if (threadIdx.x < nbuckets && cnt[threadIdx.x] > 0) {
-    const int64_t k0 = (int64_t)threadIdx.x << shift;
-    base[threadIdx.x] = key_start[k0 < K ? k0 : K] + atomicAdd(&bucket_cur[threadIdx.x], cnt[threadIdx.x]);
+  {  // B: exclusive scan of cnt[0..255] (one value per thread) + global reservation
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int v = cnt[threadIdx.x];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    int pre = 0;
+#pragma unroll
+    for (int w = 0; w < PT_T / 32; w++) pre += w < wid ? wsum[w] : 0;
+    off[threadIdx.x] = pre + inc - v;
+    if (threadIdx.x < nbuckets && v > 0) {
+      const int64_t k0 = (int64_t)threadIdx.x << shift;
+      base[threadIdx.x] = key_start[k0 < K ? k0 : K] + atomicAdd(&bucket_cur[threadIdx.x], v);
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int e = 0; e < E; e++) {
     if (br[e] >= 0) {
-      const int64_t i = c0 + e * PT_T + threadIdx.x;
-      T xr, yr, zr;
-      fold3(g, i, x, y, z, xr, yr, zr);
-      point_key(g, xr, yr, zr);  // applies the periodic shift of the SWR anchor to the coordinates
-      tmp[base[br[e] >> 16] + (br[e] & 0xffff)] = make_rec<T>(xr, yr, zr, i);
+      const int b = br[e] >> 16, dest = off[b] + (br[e] & 0xffff);
+      perm[dest] = (unsigned short)(e * PT_T + threadIdx.x);
+      pbkt[dest] = (unsigned char)b;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    const int j = e * PT_T + threadIdx.x;
+    if (j < nloc) {
+      const int b = pbkt[j];
+      tmp[base[b] + (j - off[b])] = srec[perm[j]];
     }
   }
 }
