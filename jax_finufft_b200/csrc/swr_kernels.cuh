@@ -408,11 +408,12 @@ sub_done:;
 }
 
 // ==================================================================================== INTERP
-// Per-warp shared memory: the weight rows + RES[8][32] float2 partial results of a group of 8
-// points (point t, lane j at column (j + t) & 31: conflict-free for the per-point store and for
-// the per-group sums).
+// Per-warp shared memory: the weight rows + RES[8][33] float2 partial results of a group of 8
+// points (point t, lane j at [t & 7][j]; the odd row stride makes both the per-point store and
+// the per-group sums -- lane (row, part) adds columns part*8 .. part*8+7 of its row -- free of
+// bank conflicts with constant per-lane offsets).
 template <int NS> struct SwrInterpSmem {
-  static constexpr size_t warp_floats = SwrCfg<NS>::PB * SwrCfg<NS>::ROW + 2 * 8 * 32;
+  static constexpr size_t warp_floats = SwrCfg<NS>::PB * SwrCfg<NS>::ROW + 2 * 8 * 33;  // multiple of 4 floats: rows stay 16-byte aligned
   static constexpr size_t bytes() { return SwrCfg<NS>::WARPS * warp_floats * sizeof(float); }
 };
 
@@ -427,6 +428,8 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
   if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
   float *rows = swr_smem + w * SwrInterpSmem<NS>::warp_floats;
   float2 *RES = reinterpret_cast<float2 *>(rows + C::PB * C::ROW);
+  float2 *res_w = RES + lane;                                 // + (t & 7) * 33 per point
+  const float2 *res_r = RES + (lane & 7) * 33 + (lane >> 3) * 8;  // this lane's 8 terms of the group sum
   float2 *cout = a.cout + (int64_t)blockIdx.y * a.M;
 
   const int r = lane >> 3, q = lane & 7;
@@ -541,15 +544,14 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     if constexpr (PH < D) {                                                                     \
       while (t < nb && zw == cur) {                                                             \
         const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
-        RES[(t & 7) * 32 + ((lane + t) & 31)] = point(std::integral_constant<int, PH>{}, ron);  \
+        res_w[(t & 7) * 33] = point(std::integral_constant<int, PH>{}, ron);                    \
         if ((t & 7) == 7 || t == nb - 1) {                                                      \
           /* group of <= 8 points done: lane j sums quarter j>>3 of row j&7, two butterfly */   \
           /* steps finish the row; point 8g + row lives in lane 8g + row, which keeps it */     \
           __syncwarp();                                                                         \
-          const int row8 = lane & 7, part = lane >> 3;                                          \
-          float2 s0 = make_float2(0.f, 0.f);                                                    \
-          _Pragma("unroll") for (int j = 0; j < 8; j++)                                         \
-              s0 = add2(s0, RES[row8 * 32 + ((part * 8 + j + row8) & 31)]);                     \
+          const int part = lane >> 3;                                                           \
+          float2 s0 = res_r[0];                                                                 \
+          _Pragma("unroll") for (int j = 1; j < 8; j++) s0 = add2(s0, res_r[j]);                \
           s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 8);                                        \
           s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 8);                                        \
           s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);                                       \
