@@ -215,25 +215,61 @@ __device__ __forceinline__ PtRec<T> make_rec(T xr, T yr, T zr, int64_t i) {
   return r;
 }
 
-// P0: key histogram.  One RED per distinct key per warp (clustered inputs do not serialise).
+// P0: key histogram.  One RED per distinct key per warp (__match_any_sync).  Keys that repeat
+// inside a warp mean clustered input: a few hundred hot keys would then take ~1e8 / 20 REDs on the
+// same few L2 sectors (measured 5.3 ms at C3-clustered vs 0.96 ms uniform, same-address REDs
+// retire every ~50 ns).  Such keys are first summed per CTA in a small shared-memory hash table
+// and reach L2 once per (CTA, key); `dupes` counts the merged lanes so that the placement pass can
+// pick its clustered variant without a host round trip.  Uniform input never takes that path.
+constexpr int HT_N = 1024;   // entries of the per-CTA hot-key table (power of two)
+constexpr int HT_EMPTY = -1;
+__device__ __forceinline__ int ht_slot(int key) { return (int)(((unsigned)key * 2654435761u) >> 22); }  // 10 bits
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T *__restrict__ x,
                                                    const T *__restrict__ y, const T *__restrict__ z,
-                                                   int32_t *__restrict__ hist) {
+                                                   int32_t *__restrict__ hist, int32_t *__restrict__ dupes) {
+  __shared__ int tkey[HT_N], tcnt[HT_N];
+  __shared__ int used;
+  for (int i = threadIdx.x; i < HT_N; i += blockDim.x) { tkey[i] = HT_EMPTY; tcnt[i] = 0; }
+  if (threadIdx.x == 0) used = 0;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t Mpad = (M + 31) & ~int64_t(31);
+  int merged = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Mpad; i += stride) {
     const bool valid = i < M;
-    int key = -1 - lane;  // unique dummy key for tail lanes
+    int key = -2 - lane;  // unique dummy key for tail lanes
     if (valid) {
       T xr, yr, zr;
       fold3(g, i, x, y, z, xr, yr, zr);
       key = point_key(g, xr, yr, zr);
     }
     const unsigned peers = __match_any_sync(0xffffffffu, key);
-    if (valid && lane == __ffs(peers) - 1) atomicAdd(&hist[key], __popc(peers));
+    if (valid && lane == __ffs(peers) - 1) {
+      const int n = __popc(peers);
+      bool done = false;
+      if (n > 1) {  // hot key: sum it in the CTA's table (3 probes, then straight to L2)
+        merged += n - 1;
+        int h = ht_slot(key);
+        for (int pr = 0; pr < 3 && !done; pr++, h = (h + 1) & (HT_N - 1)) {
+          const int old = atomicCAS(&tkey[h], HT_EMPTY, key);
+          if (old == HT_EMPTY || old == key) {
+            atomicAdd(&tcnt[h], n);
+            if (old == HT_EMPTY) used = 1;
+            done = true;
+          }
+        }
+      }
+      if (!done) atomicAdd(&hist[key], n);
+    }
   }
+  if (merged) atomicAdd(dupes, merged);
+  __syncthreads();
+  if (used)
+    for (int i = threadIdx.x; i < HT_N; i += blockDim.x)
+      if (tkey[i] != HT_EMPTY) atomicAdd(&hist[tkey[i]], tcnt[i]);
 }
 
 // P1: CTA-local partition of a chunk into buckets of consecutive keys (bucket = key >> shift).
@@ -333,7 +369,9 @@ __global__ void __launch_bounds__(256) k_place(SortGeom g, int64_t M, const T *_
                                                 const T *__restrict__ y, const T *__restrict__ z,
                                                 const PtRec<T> *__restrict__ tmp,
                                                 int32_t *__restrict__ key_cursor,
-                                                PtRec<T> *__restrict__ out) {
+                                                PtRec<T> *__restrict__ out,
+                                                const int32_t *__restrict__ dupes, int64_t dupe_limit) {
+  if (dupes && *dupes > dupe_limit) return;  // clustered input: k_place_agg does the work
   const int lane = threadIdx.x & 31;
   const int64_t c0 = (int64_t)blockIdx.x * (256 * PL_E);
   for (int e0 = 0; e0 < PL_E; e0 += PL_G) {
@@ -374,6 +412,96 @@ __global__ void __launch_bounds__(256) k_place(SortGeom g, int64_t M, const T *_
   }
 }
 
+// P2, clustered input (dupes > dupe_limit): a CTA takes PA_N consecutive records, sums the
+// multiplicity of every key in a shared-memory hash table (each record remembers its table entry
+// and its rank inside the CTA), reserves one run per (CTA, key) with a single global atomicAdd,
+// and re-reads the records (L2) to place them.  Global atomics per hot key drop from one per warp
+// to one per PA_N records.  Keys that do not fit the table fall back to their own global atomic.
+constexpr int PA_T = 512, PA_E = 32, PA_N = PA_T * PA_E;  // 16384 records per CTA
+constexpr int PA_HT = 4096;
+template <typename T, bool RAW>
+__global__ void __launch_bounds__(PA_T) k_place_agg(SortGeom g, int64_t M, const T *__restrict__ x,
+                                                     const T *__restrict__ y, const T *__restrict__ z,
+                                                     const PtRec<T> *__restrict__ tmp,
+                                                     int32_t *__restrict__ key_cursor,
+                                                     PtRec<T> *__restrict__ out,
+                                                     const int32_t *__restrict__ dupes, int64_t dupe_limit) {
+  if (*dupes <= dupe_limit) return;
+  extern __shared__ int pa_smem[];
+  int *tkey = pa_smem, *tcnt = pa_smem + PA_HT;        // cnt doubles as the reserved base in phase 3
+  unsigned *slot = (unsigned *)(pa_smem + 2 * PA_HT);  // per record: entry << 16 | rank (0xffffffff: direct)
+  for (int i = threadIdx.x; i < PA_HT; i += PA_T) { tkey[i] = HT_EMPTY; tcnt[i] = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t c0 = (int64_t)blockIdx.x * PA_N;
+  auto load = [&](int64_t i) {
+    if (RAW) {
+      T xr, yr, zr;
+      fold3(g, i, x, y, z, xr, yr, zr);
+      return make_rec<T>(xr, yr, zr, i);
+    }
+    return tmp[i];
+  };
+  for (int e = 0; e < PA_E; e++) {
+    const int sl = e * PA_T + threadIdx.x;
+    const int64_t i = c0 + sl;
+    if (i - lane >= M) break;
+    int key = -2 - lane;
+    if (i < M) {
+      PtRec<T> r = load(i);
+      key = point_key(g, r.x, r.y, r.z);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1, n = __popc(peers);
+    unsigned v = 0xffffffffu;
+    if (i < M && lane == leader) {
+      int h = (int)(((unsigned)key * 2654435761u) >> 20);  // 12 bits
+      for (int pr = 0; pr < 4; pr++, h = (h + 1) & (PA_HT - 1)) {
+        const int old = atomicCAS(&tkey[h], HT_EMPTY, key);
+        if (old == HT_EMPTY || old == key) {
+          const int r0 = atomicAdd(&tcnt[h], n);
+          if (r0 + n <= 0xffff) v = ((unsigned)h << 16) | (unsigned)r0; else atomicSub(&tcnt[h], n);
+          break;
+        }
+      }
+    }
+    v = __shfl_sync(0xffffffffu, v, leader);
+    if (i < M) slot[sl] = v == 0xffffffffu ? v : v + (unsigned)__popc(peers & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PA_HT; i += PA_T)
+    if (tkey[i] != HT_EMPTY && tcnt[i] > 0) tcnt[i] = atomicAdd(&key_cursor[tkey[i]], tcnt[i]);
+  __syncthreads();
+  for (int e = 0; e < PA_E; e++) {
+    const int sl = e * PA_T + threadIdx.x;
+    const int64_t i = c0 + sl;
+    if (i - lane >= M) break;
+    PtRec<T> r;
+    int key = -2 - lane;
+    unsigned v = 0;
+    if (i < M) {
+      r = load(i);
+      v = slot[sl];
+      if (v == 0xffffffffu) key = point_key(g, r.x, r.y, r.z);
+    }
+    // records whose key found no table entry: one global atomic per distinct key per warp
+    const unsigned direct = __ballot_sync(0xffffffffu, i < M && v == 0xffffffffu);
+    int pos = 0;
+    if (direct) {
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      const int leader = __ffs(peers) - 1;
+      int b = 0;
+      if (key >= 0 && lane == leader) b = atomicAdd(&key_cursor[key], __popc(peers));
+      b = __shfl_sync(0xffffffffu, b, leader);
+      pos = b + __popc(peers & ((1u << lane) - 1u));
+    }
+    if (i < M) {
+      if (v != 0xffffffffu) pos = tcnt[v >> 16] + (int)(v & 0xffff);
+      out[pos] = r;
+    }
+  }
+}
+
 // gpu_sort = 0: identity permutation, folded coordinates only
 template <typename T>
 __global__ void __launch_bounds__(256) k_fold_only(SortGeom g, int64_t M, const T *__restrict__ x,
@@ -405,14 +533,19 @@ __global__ void k_sp_count(int64_t nbins, int nsub, const int32_t *__restrict__ 
     if (b < nbins) cnt[b] = (key_start[(b + 1) * nsub] - s + maxsub - 1) / maxsub;
   }
 }
-// subproblem -> bin map   (precision_independent.cu:83-91)
+// subproblem -> bin map   (precision_independent.cu:83-91); one thread per subproblem slot finds
+// its bin by bisection (a bin with thousands of subproblems -- clustered input -- used to be
+// filled by a single thread)
 __global__ void k_sp_fill(int64_t nbins, const int32_t *__restrict__ sp_off,
                           int32_t *__restrict__ sp_bin, int64_t cap) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < nbins) {
-    const int e = sp_off[b + 1];
-    for (int s = sp_off[b]; s < e && s < cap; s++) sp_bin[s] = (int32_t)b;
+  const int64_t sp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sp >= cap || sp >= sp_off[nbins]) return;
+  int64_t lo = 0, hi = nbins;  // largest b with sp_off[b] <= sp
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (sp_off[mid] <= sp) lo = mid; else hi = mid;
   }
+  sp_bin[sp] = (int32_t)lo;
 }
 
 template <typename U> static int grow(U **p, int64_t *cap, int64_t need, cudaStream_t st) {
@@ -472,14 +605,17 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     ps.cap_bins = nbins;
   }
   if (!ps.bucket_cur)
-    if (int e = dev_alloc_t(&ps.bucket_cur, 256, st)) return e;
+    if (int e = dev_alloc_t(&ps.bucket_cur, 256 + 8, st)) return e;
   const int64_t sp_cap = std::min<int64_t>(nbins, M) + M / p.maxsub + 1;
   if (int e = grow(&ps.sp_bin, &ps.cap_sp, sp_cap, st)) return e;
   ps.sp_cap = sp_cap;
 
   // P0 + scan
   B2N_CUDA_OK(cudaMemsetAsync(ps.key_cnt, 0, sizeof(int32_t) * K, st));
-  if (M > 0) k_key_hist<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.key_cnt);  B2N_LAUNCHED(1);
+  int32_t *dupes = ps.bucket_cur + 256;  // lanes merged by the histogram pass (clustering signal)
+  B2N_CUDA_OK(cudaMemsetAsync(dupes, 0, sizeof(int32_t), st));
+  const int64_t dupe_limit = M / 8;
+  if (M > 0) k_key_hist<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.key_cnt, dupes);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   if (int e = exclusive_scan_i32(ps.key_cnt, ps.key_start, K, st)) return e;
 
@@ -491,7 +627,7 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     const int nb_blk = cdiv(nbins + 1, 256);
     k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, g.nsub, ps.key_start, p.maxsub, ps.bin_start, ps.key_cnt);  B2N_LAUNCHED(1);
     if (int e = exclusive_scan_i32(ps.key_cnt, ps.sp_off, nbins, st)) return e;
-    k_sp_fill<<<nb_blk, 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);  B2N_LAUNCHED(1);
+    k_sp_fill<<<cdiv(sp_cap, 256), 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);  B2N_LAUNCHED(1);
     B2N_LAUNCH_OK();
   }
 
@@ -503,16 +639,21 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   const int nbuckets = (int)(((K - 1) >> shift) + 1);
   if (M > 0) {
     const int nplace = cdiv(M, 256 * PL_E);
+    const size_t pa_smem = (2 * PA_HT + PA_N) * sizeof(int);
+    B2N_CUDA_OK(cudaFuncSetAttribute(k_place_agg<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pa_smem));
+    B2N_CUDA_OK(cudaFuncSetAttribute(k_place_agg<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pa_smem));
     if (nbuckets > 1) {
       if (int e = grow(&ps.tmp, &ps.cap_tmp, M, st)) return e;
       B2N_CUDA_OK(cudaMemsetAsync(ps.bucket_cur, 0, sizeof(int32_t) * 256, st));
       k_partition<T><<<cdiv(M, PT_T * PartCfg<T>::E), PT_T, 0, st>>>(g, M, x, y, z, ps.key_start, K, shift,
                                                                    nbuckets, ps.bucket_cur, ps.tmp);
-      k_place<T, false><<<nplace, 256, 0, st>>>(g, M, x, y, z, ps.tmp, ps.key_start, ps.rec);
-      B2N_LAUNCHED(2);
+      k_place<T, false><<<nplace, 256, 0, st>>>(g, M, x, y, z, ps.tmp, ps.key_start, ps.rec, dupes, dupe_limit);
+      k_place_agg<T, false><<<cdiv(M, PA_N), PA_T, pa_smem, st>>>(g, M, x, y, z, ps.tmp, ps.key_start, ps.rec, dupes, dupe_limit);
+      B2N_LAUNCHED(3);
     } else {
-      k_place<T, true><<<nplace, 256, 0, st>>>(g, M, x, y, z, nullptr, ps.key_start, ps.rec);
-      B2N_LAUNCHED(1);
+      k_place<T, true><<<nplace, 256, 0, st>>>(g, M, x, y, z, nullptr, ps.key_start, ps.rec, dupes, dupe_limit);
+      k_place_agg<T, true><<<cdiv(M, PA_N), PA_T, pa_smem, st>>>(g, M, x, y, z, nullptr, ps.key_start, ps.rec, dupes, dupe_limit);
+      B2N_LAUNCHED(2);
     }
     B2N_LAUNCH_OK();
   }

@@ -141,8 +141,9 @@ def test_type3_mid_vs_oracle(dim):
         assert oracle.relerr(f, fr) < 2 * eps + 2.5e-7 * 43 * np.pi * np.sqrt(dim)
 
 
+@pytest.mark.parametrize("dist", ["uniform", "clustered", "mixed"])
 @pytest.mark.parametrize("method", [2, 0])
-def test_binsort_contract_vs_oracle(method):
+def test_binsort_contract_vs_oracle(method, dist):
     """SURVEY.md §0.7: histogram, exclusive-scan offsets and per-bin point SETS must match;
     the order inside a bin is unspecified in the reference (atomicAdd ranks).  gpu_method=2 (tile
     kernels) bins by floor(x') exactly like the reference; the default 3-D float path (sliding-
@@ -152,6 +153,16 @@ def test_binsort_contract_vs_oracle(method):
     rng = np.random.default_rng(11)
     M, nm = 300000, (40, 36, 30)
     pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(3)]
+    if dist != "uniform":
+        # SURVEY.md §8(d) "clustered": iid uniform in a corner box 8 fine-grid cells wide -- every warp
+        # of the sort sees repeated keys, which switches the histogram to its per-CTA hot-key table
+        # and the placement pass to its aggregated variant (sort.cu); "mixed" = half and half
+        n = M if dist == "clustered" else M // 2
+        for d in range(3):
+            h = 2 * np.pi / (2 * nm[d])
+            pts[d][:n] = (-np.pi + rng.uniform(0, 8 * h, n)).astype(np.float32)
+        perm = rng.permutation(M)
+        pts = [x[perm] for x in pts]
     pts[0][:5] = [-np.pi, np.pi, np.nextafter(np.float32(np.pi), np.float32(0)), 0.0, 3 * np.pi]
     pts[1][:5] = pts[0][:5]
     pts[2][:5] = pts[0][:5]
