@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
                                                    const T *__restrict__ y, const T *__restrict__ z,
                                                    int32_t *__restrict__ hist, int32_t *__restrict__ dupes) {
   __shared__ int tkey[HT_N], tcnt[HT_N];
-  __shared__ int used;
+  __shared__ int used;  // lanes merged in this CTA (> 0 <=> the table may hold entries)
   for (int i = threadIdx.x; i < HT_N; i += blockDim.x) { tkey[i] = HT_EMPTY; tcnt[i] = 0; }
   if (threadIdx.x == 0) used = 0;
   __syncthreads();
@@ -247,17 +247,19 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
       key = point_key(g, xr, yr, zr);
     }
     const unsigned peers = __match_any_sync(0xffffffffu, key);
+    // any repeated key in the warp = clustered input: then EVERY key of the warp goes through the
+    // table (with a few hundred hot keys most of them still appear once per warp)
+    const bool hot = __any_sync(0xffffffffu, valid && __popc(peers) > 1);
     if (valid && lane == __ffs(peers) - 1) {
       const int n = __popc(peers);
       bool done = false;
-      if (n > 1) {  // hot key: sum it in the CTA's table (3 probes, then straight to L2)
+      if (hot) {  // sum it in the CTA's table (3 probes, then straight to L2)
         merged += n - 1;
         int h = ht_slot(key);
         for (int pr = 0; pr < 3 && !done; pr++, h = (h + 1) & (HT_N - 1)) {
           const int old = atomicCAS(&tkey[h], HT_EMPTY, key);
           if (old == HT_EMPTY || old == key) {
             atomicAdd(&tcnt[h], n);
-            if (old == HT_EMPTY) used = 1;
             done = true;
           }
         }
@@ -265,8 +267,9 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
       if (!done) atomicAdd(&hist[key], n);
     }
   }
-  if (merged) atomicAdd(dupes, merged);
+  if (merged) atomicAdd(&used, merged);  // CTA total first: `dupes` is ONE address for the whole grid
   __syncthreads();
+  if (threadIdx.x == 0 && used > 0) atomicAdd(dupes, used);
   if (used)
     for (int i = threadIdx.x; i < HT_N; i += blockDim.x)
       if (tkey[i] != HT_EMPTY) atomicAdd(&hist[tkey[i]], tcnt[i]);
