@@ -114,43 +114,60 @@ template <typename T> int deconvolve(Plan<T> &p, const cpx<T> *fw, cpx<T> *fk, i
   return 0;
 }
 
-// One pass over the fine grid: every cell gets either its amplified mode or zero.
+// One pass over the fine grid: every cell gets either its amplified mode or zero.  A CTA owns a
+// 512-cell piece of one fine-grid row: the row's (y, z) decode and mode test happen once per CTA
+// with 32-bit arithmetic, three rows out of four (3-D) are pure zero fill, and every thread
+// stores two adjacent cells as one 16-byte word.  (The first version decoded each cell with
+// 64-bit divisions: 0.60 ms for 1.15 GB at C3, issue-bound at 29 % of the HBM roofline.)
+constexpr int AMP_T = 256;
 template <typename T>
-__global__ void __launch_bounds__(256) k_amplify(const ModeGeom g, cpx<T> *__restrict__ fw,
-                                                  const cpx<T> *__restrict__ fk,
-                                                  const T *__restrict__ h1, const T *__restrict__ h2,
-                                                  const T *__restrict__ h3, int64_t nmodes,
-                                                  int64_t nftot) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nftot) return;
-  fw += (int64_t)blockIdx.y * nftot;
+__global__ void __launch_bounds__(AMP_T) k_amplify(const ModeGeom g, cpx<T> *__restrict__ fw,
+                                                    const cpx<T> *__restrict__ fk,
+                                                    const T *__restrict__ h1, const T *__restrict__ h2,
+                                                    const T *__restrict__ h3, int64_t nmodes,
+                                                    int64_t nftot, int nxchunk) {
+  const unsigned row = blockIdx.x / (unsigned)nxchunk;
+  const int xc = (int)(blockIdx.x - row * (unsigned)nxchunk);
+  fw += (int64_t)blockIdx.y * nftot + (int64_t)row * g.nf[0];
   fk += (int64_t)blockIdx.y * nmodes;
-  const int w1 = (int)(i % g.nf[0]);
-  const int64_t r = i / g.nf[0];
-  int a1, a2, a3;
-  cpx<T> o;
-  o.x = o.y = T(0);
-  const int k1 = fine_to_mode(w1, g.ms[0], g.nf[0], g.modeord, a1);
-  int k2 = 0, k3 = 0;
-  bool ok = k1 >= 0;
-  T kv = T(1);
-  if (ok) kv = h1[a1];
-  if (ok && g.dim > 1) {
-    k2 = fine_to_mode((int)(r % g.nf[1]), g.ms[1], g.nf[1], g.modeord, a2);
-    ok = k2 >= 0;
-    if (ok) kv *= h2[a2];
+  int a2 = 0, a3 = 0, k2 = 0, k3 = 0;
+  bool rowok = true;
+  if (g.dim > 1) {
+    const unsigned w3 = row / (unsigned)g.nf[1], w2 = row - w3 * (unsigned)g.nf[1];
+    k2 = fine_to_mode((int)w2, g.ms[1], g.nf[1], g.modeord, a2);
+    rowok = k2 >= 0;
+    if (rowok && g.dim > 2) {
+      k3 = fine_to_mode((int)w3, g.ms[2], g.nf[2], g.modeord, a3);
+      rowok = k3 >= 0;
+    }
   }
-  if (ok && g.dim > 2) {
-    k3 = fine_to_mode((int)(r / g.nf[1]), g.ms[2], g.nf[2], g.modeord, a3);
-    ok = k3 >= 0;
-    if (ok) kv *= h3[a3];
+  const int w1 = xc * (2 * AMP_T) + 2 * threadIdx.x;  // nf[0] is even for every grid the library builds
+  if (w1 >= g.nf[0]) return;
+  cpx<T> o[2];
+  o[0].x = o[0].y = o[1].x = o[1].y = T(0);
+  if (rowok) {
+    const T hv2 = g.dim > 1 ? h2[a2] : T(1), hv3 = g.dim > 2 ? h3[a3] : T(1);
+    const cpx<T> *fkrow = fk + ((int64_t)k3 * g.ms[1] + k2) * g.ms[0];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      int a1;
+      const int k1 = fine_to_mode(w1 + e, g.ms[0], g.nf[0], g.modeord, a1);
+      if (k1 >= 0) {
+        T kv = h1[a1];  // same association as the reference: ((h1 * h2) * h3)
+        if (g.dim > 1) kv *= hv2;
+        if (g.dim > 2) kv *= hv3;
+        const cpx<T> v = fkrow[k1];
+        o[e].x = v.x / kv;
+        o[e].y = v.y / kv;
+      }
+    }
   }
-  if (ok) {
-    const cpx<T> v = fk[((int64_t)k3 * g.ms[1] + k2) * g.ms[0] + k1];
-    o.x = v.x / kv;
-    o.y = v.y / kv;
+  if (sizeof(T) == 4 && (g.nf[0] & 1) == 0) {
+    *reinterpret_cast<float4 *>(fw + w1) = make_float4((float)o[0].x, (float)o[0].y, (float)o[1].x, (float)o[1].y);
+  } else {
+    fw[w1] = o[0];
+    if (w1 + 1 < g.nf[0]) fw[w1 + 1] = o[1];
   }
-  fw[i] = o;
 }
 
 template <typename T> int amplify(Plan<T> &p, cpx<T> *fw, const cpx<T> *fk, int ntr) {
@@ -158,9 +175,12 @@ template <typename T> int amplify(Plan<T> &p, cpx<T> *fw, const cpx<T> *fk, int 
   g.dim = p.dim;
   g.modeord = p.opts.modeord;
   for (int d = 0; d < 3; d++) { g.ms[d] = (int)p.ms[d]; g.nf[d] = (int)p.nf[d]; }
-  dim3 grid((unsigned)cdiv(p.nftot, 256), (unsigned)ntr);
-  k_amplify<T><<<grid, 256, 0, p.stream>>>(g, fw, fk, p.fwker[0], p.fwker[1], p.fwker[2], p.nmodes,
-                                           p.nftot);  B2N_LAUNCHED(1);
+  const int nxchunk = cdiv(p.nf[0], 2 * AMP_T);
+  const int64_t rows = p.nftot / p.nf[0];
+  if (rows * nxchunk > 0x7fffffffLL) return B2N_ERR_NDATA_NOTVALID;
+  dim3 grid((unsigned)(rows * nxchunk), (unsigned)ntr);
+  k_amplify<T><<<grid, AMP_T, 0, p.stream>>>(g, fw, fk, p.fwker[0], p.fwker[1], p.fwker[2], p.nmodes,
+                                             p.nftot, nxchunk);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   return 0;
 }
