@@ -171,7 +171,7 @@ int Plan<T>::init(int type_, int dim_, const int64_t *n_modes, int iflag_, int n
   for (int d = 0; d < 3; d++) base_bin[d] = bin[d];
   // sliding-window register kernels: 3-D float, ns <= 8, method auto or 3 ("no shared atomics",
   // the niche of the reference's output-driven method), default bins
-  swr_ok = sizeof(T) == 4 && dim == 3 && ns <= 8 && method == 2 &&
+  swr_ok = sizeof(T) == 4 && (dim == 3 || dim == 2) && ns <= 8 && method == 2 &&
            (opts.gpu_method == 0 || opts.gpu_method == 3) && opts.gpu_binsizex <= 0 &&
            opts.gpu_binsizey <= 0 && opts.gpu_binsizez <= 0;
 
@@ -247,12 +247,13 @@ int Plan<T>::setpts(int64_t M, const void *x, const void *y, const void *z, int6
 // register window per subproblem, which only amortises on reasonably dense point sets.
 template <typename T> void Plan<T>::set_geometry(int64_t M) {
   static const char *force = getenv("B2N_FORCE_METHOD");
-  bool swr = swr_ok && nf[0] % 2 == 0 && nf[0] >= 32 && nf[1] >= 32 && nf[2] >= 32 &&
-             (double)M >= 0.08 * (double)nftot;
+  // dense enough to fill the bins: 3-D bins hold 2 x 6 x 64 anchor cells, 2-D bins (17 - ns)^2
+  bool swr = swr_ok && nf[0] % 2 == 0 && nf[0] >= 32 && nf[1] >= 32 &&
+             (dim == 3 ? nf[2] >= 32 && (double)M >= 0.08 * (double)nftot : (double)M >= 0.25 * (double)nftot);
   if (force && swr_ok) swr = force[0] == '3';
   if (swr) {
     method = 3;
-    swr_bins(ns, bin);
+    swr_bins(dim, ns, bin);
     maxsub = opts.gpu_maxsubprobsize > 0 ? opts.gpu_maxsubprobsize : 2048;
   } else {
     method = base_method;

@@ -65,7 +65,7 @@ template <typename T> struct Plan : PlanBase {
   int type = 0, dim = 0, iflag = 1, ntransf = 1, batch = 1;
   double eps = 0;
   b2n_opts opts;
-  int method = 0;  // 1 = GM kernels, 2 = tile kernels, 3 = sliding-window register kernels (SWR)
+  int method = 0;  // 1 = GM kernels, 2 = tile kernels, 3 = register kernels (3-D sliding window, 2-D tile)
   int ns = 0, ncoef = 0;
   double beta = 0, sigma = 2.0;
   int warn = 0;
@@ -142,8 +142,8 @@ int interp_tile(Plan<T> &p, cpx<T> *c, const cpx<T> *postscale, const cpx<T> *fw
 template <typename T>
 int interp_gm(Plan<T> &p, cpx<T> *c, const cpx<T> *postscale, const cpx<T> *fw, int ntr);
 
-// sliding-window register kernels (swr.cu): 3-D float, ns <= 8, bins from swr_bins()
-void swr_bins(int ns, int *bin);
+// register kernels (swr.cu): sliding window (3-D) / register tile (2-D), float, ns <= 8, bins from swr_bins()
+void swr_bins(int dim, int ns, int *bin);
 int spread_swr(Plan<float> &p, const float2 *c, const float2 *prescale, float2 *fw, int ntr);
 int interp_swr(Plan<float> &p, float2 *c, const float2 *postscale, const float2 *fw, int ntr);
 

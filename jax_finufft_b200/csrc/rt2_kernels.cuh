@@ -1,0 +1,297 @@
+// rt2_kernels.cuh -- register-TILE spreading / interpolation, 2-D, float, ns <= 8.
+// Replaces spread_2d_subprob and interp_2d_nupts_driven / interp_2d_subprob
+// (V/src/cuda/2d/spreadinterp2d.cuh:116-200, 203-330) on the 2-D c64 paths (BASELINE configs C2
+// and C4) when the point set is dense enough to fill the bins.
+//
+// Same idea as the 3-D sliding-window kernels (swr_kernels.cuh) with the ring dropped, because a
+// 2-D window is small enough to live in registers whole:
+//   * points are binned by the ANCHOR cell of their ns-wide stencil (sort.cu, swr geometry), bins
+//     of BX x BY = (17 - ns)^2 anchor cells (10 x 10 at ns = 7); no sub-key, any order in a bin;
+//   * ONE WARP owns a subproblem (<= maxsub points of one bin) and the 16 x 16 fine-grid cells it
+//     can touch: lane (r, q) holds x cells {2q, 2q+1} of rows {r, r+4, r+8, r+12} -- 8 complex
+//     accumulators per lane, all indices literals;
+//   * per batch of 32 points lane t evaluates the two kernel vectors of point t (FFMA2 Horner)
+//     and parks them in warp-private shared memory as the inner loop consumes them: strength *
+//     x-weight pairs per window column (zero outside the stencil), y weights duplicated (w, w) in
+//     [row mod 4][row / 4] order (zero outside);
+//   * per point the warp issues 3 LDS.128 + 8 FFMA2 (spread) -- cells outside the point's stencil
+//     multiply by zero -- with the same rolling reloads as the 3-D kernel;
+//   * the tile is added to the fine grid ONCE per subproblem with red.global.add.v2.f32.
+// The tile kernels they replace (tile_kernels.cuh) do an LDS.128 + STS.128 read-modify-write of
+// shared memory per touched row segment; measured 1.28 ms per 1e7-point transform at C4 (2-D
+// type 1, ns = 7), 35x off the HBM bound of (4d+12) M + 8 nf bytes.
+//
+// Interpolation: the tile is LOADED into registers once per subproblem; per point 8 FFMA2 fold
+// the x weights in, 4 more the y weights; partial results of 8 points are transposed through a
+// padded shared-memory tile exactly as in the 3-D kernel.
+#pragma once
+#include "swr_kernels.cuh"
+
+namespace b2n {
+
+template <int NS> struct Rt2Cfg {
+  static constexpr int CX = 2, S = 4;
+  static constexpr int WX = 8 * CX, WY = 4 * S;       // 16 x 16 window
+  static constexpr int H = NS / 2;
+  static constexpr int BX = WX - NS + 1, BY = WY - NS + 1;
+  static constexpr int PB = 32;
+  static constexpr int NP = (NS + 1) / 2;
+  static constexpr int KXO = 0;                        // WX pairs: spread (c.re kx, c.im kx); interp (kx, kx)
+  static constexpr int KYO = 2 * WX;                   // [r = row & 3][s = row >> 2] pairs (ky, ky)
+  static constexpr int ROW0 = KYO + 2 * WY;            // 64 floats
+  static constexpr int ROW = ROW0 + 4;                 // stride / 4 odd
+  static constexpr int WARPS = 4;
+  static constexpr size_t spread_smem() { return (size_t)WARPS * PB * ROW * sizeof(float); }
+  static constexpr size_t interp_warp_floats = PB * ROW + 2 * 8 * 33;
+  static constexpr size_t interp_smem() { return (size_t)WARPS * interp_warp_floats * sizeof(float); }
+  static_assert(BX >= 1 && BY >= 1, "window too small");
+};
+
+// lane t parks the weights of one point: pr4 = record, cv = strength (spread) or (1, 1) (interp)
+template <int NS>
+__device__ __forceinline__ void rt2_weights(const HornerTable<float> &tab, const float4 pr4, float2 cv,
+                                            int xa, int ya, float *row) {
+  using C = Rt2Cfg<NS>;
+  constexpr int NP = C::NP;
+  const float px = pr4.x, py = pr4.y;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < C::ROW0 / 4; i++) reinterpret_cast<float4 *>(row)[i] = z4;
+  const int isx = window_start(px, NS), isy = window_start(py, NS);
+  float kx[2 * NP], ky[2 * NP];
+  if (!tab.direct) {
+    const float zx = fmaf(2.f, float(isx) - px, float(NS - 1));
+    const float zy = fmaf(2.f, float(isy) - py, float(NS - 1));
+    const float2 zx2 = make_float2(zx, zx), zy2 = make_float2(zy, zy);
+    float2 ax[NP], ay[NP];
+#pragma unroll
+    for (int j = 0; j < NP; j++) ax[j] = ay[j] = make_float2(tab.c[0][2 * j], tab.c[0][2 * j + 1]);
+    for (int k = 1; k < tab.ncoef; k++) {
+#pragma unroll
+      for (int j = 0; j < NP; j++) {
+        const float2 cj = make_float2(tab.c[k][2 * j], tab.c[k][2 * j + 1]);
+        ax[j] = fma2(ax[j], zx2, cj);
+        ay[j] = fma2(ay[j], zy2, cj);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+      kx[2 * j] = ax[j].x; kx[2 * j + 1] = ax[j].y;
+      ky[2 * j] = ay[j].x; ky[2 * j + 1] = ay[j].y;
+    }
+  } else {
+    float tx[NS], ty[NS];
+    eval_kernel<float, NS>(tx, float(isx) - px, tab);
+    eval_kernel<float, NS>(ty, float(isy) - py, tab);
+#pragma unroll
+    for (int j = 0; j < NS; j++) { kx[j] = tx[j]; ky[j] = ty[j]; }
+  }
+  {
+    int xl = isx - xa;
+    xl = xl < 0 ? 0 : (xl > C::WX - NS ? C::WX - NS : xl);
+    float2 *dst = reinterpret_cast<float2 *>(row + C::KXO) + xl;
+#pragma unroll
+    for (int j = 0; j < NS; j++) dst[j] = make_float2(cv.x * kx[j], cv.y * kx[j]);
+  }
+  {
+    int yl = isy - ya;
+    yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
+    float2 *dst = reinterpret_cast<float2 *>(row + C::KYO);
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+      const int iy = yl + j;
+      dst[C::S * (iy & 3) + (iy >> 2)] = make_float2(ky[j], ky[j]);
+    }
+  }
+}
+
+// this lane's share of one point's row: x pairs of its two cells, (ky, ky) of its four rows
+struct Rt2Row {
+  float4 cx;      // pairs of cells 2q, 2q+1
+  float4 ky[2];   // pairs of rows r, r+4 | r+8, r+12
+  __device__ __forceinline__ void load_x(const float *myx, int ro) { cx = *reinterpret_cast<const float4 *>(myx + ro); }
+  __device__ __forceinline__ void load_y(const float *myy, int ro, int i) {
+    ky[i] = *reinterpret_cast<const float4 *>(myy + ro + 4 * i);
+  }
+  __device__ __forceinline__ float2 cxp(int c) const { return c ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y); }
+  __device__ __forceinline__ float2 kyp(int s) const {
+    return (s & 1) ? make_float2(ky[s >> 1].z, ky[s >> 1].w) : make_float2(ky[s >> 1].x, ky[s >> 1].y);
+  }
+};
+
+// ==================================================================================== SPREAD
+template <int NS>
+__global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
+    k_rt2_spread(const SwrArgs a, const __grid_constant__ HornerTable<float> tab) {
+  using C = Rt2Cfg<NS>;
+  constexpr int S = C::S, CX = C::CX;
+  extern __shared__ __align__(16) float swr_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int first, cnt, x0, y0;
+  if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
+  float *rows = swr_smem + w * (C::PB * C::ROW);
+  const float2 *cin = a.cin + (int64_t)blockIdx.y * a.M;
+  float2 *fw = a.fw + (int64_t)blockIdx.y * a.nftot;
+
+  const int r = lane >> 3, q = lane & 7;
+  const int xa = x0 - C::H, ya = y0 - C::H;
+  const int nf0 = a.nf[0], nf1 = a.nf[1];
+
+  float2 acc[S][CX];
+#pragma unroll
+  for (int s = 0; s < S; s++)
+#pragma unroll
+    for (int c = 0; c < CX; c++) acc[s][c] = make_float2(0.f, 0.f);
+
+  Rt2Row pr;
+  const float *myx = rows + C::KXO + 2 * CX * q;
+  const float *myy = rows + C::KYO + 2 * S * r;
+  const PtRec<float> *recp = a.rec + first + lane;
+  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto ldc = [&](const float4 &rc, float2 &sc) {
+    const int o = __float_as_int(rc.w);
+    if (a.scale) sc = __ldg(a.scale + o);
+    return ld_stream2(cin + o);
+  };
+  const float2 zero2 = make_float2(0.f, 0.f);
+  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
+  float4 recB = lane + C::PB < cnt ? ld_stream4(recp + C::PB) : zrec;
+  float2 sA = make_float2(1.f, 0.f), sB = sA;
+  float2 cA = lane < cnt ? ldc(recA, sA) : zero2;
+  for (int b0 = 0; b0 < cnt; b0 += C::PB) {
+    const int nb = min(C::PB, cnt - b0);
+    const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
+    const float2 cB = b0 + C::PB + lane < cnt ? ldc(recB, sB) : zero2;
+    __syncwarp();
+    if (lane < nb) {
+      float2 cv = cA;
+      if (a.scale) cv = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
+      rt2_weights<NS>(tab, recA, cv, xa, ya, rows + lane * C::ROW);
+    }
+    __syncwarp();
+    recA = recB;
+    recB = recC;
+    cA = cB;
+    sA = sB;
+    pr.load_x(myx, 0);
+    pr.load_y(myy, 0, 0);
+    pr.load_y(myy, 0, 1);
+    int ro = 0;
+    for (int t = 0; t < nb; t++) {
+      const int ron = t + 1 < nb ? ro + C::ROW : ro;
+      const float2 c0 = pr.cxp(0), c1 = pr.cxp(1);
+      pr.load_x(myx, ron);
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int s = 2 * i; s < 2 * i + 2; s++) {
+          const float2 k = pr.kyp(s);
+          acc[s][0] = fma2(c0, k, acc[s][0]);
+          acc[s][1] = fma2(c1, k, acc[s][1]);
+        }
+        pr.load_y(myy, ron, i);
+      }
+      ro = ron;
+    }
+  }
+  // the tile goes to the fine grid once
+#pragma unroll
+  for (int s = 0; s < S; s++) {
+    const int gy = wrap_once(ya + 4 * s + r, nf1);
+#pragma unroll
+    for (int c = 0; c < CX; c++) {
+      const int gx = wrap_once(xa + CX * q + c, nf0);
+      if (acc[s][c].x != 0.f || acc[s][c].y != 0.f) red_add(fw + (int64_t)gy * nf0 + gx, acc[s][c]);
+    }
+  }
+}
+
+// ==================================================================================== INTERP
+template <int NS>
+__global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
+    k_rt2_interp(const SwrArgs a, const __grid_constant__ HornerTable<float> tab) {
+  using C = Rt2Cfg<NS>;
+  constexpr int S = C::S, CX = C::CX;
+  extern __shared__ __align__(16) float swr_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int first, cnt, x0, y0;
+  if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
+  float *rows = swr_smem + w * C::interp_warp_floats;
+  float2 *RES = reinterpret_cast<float2 *>(rows + C::PB * C::ROW);
+  float2 *res_w = RES + lane;
+  const float2 *res_r = RES + (lane & 7) * 33 + (lane >> 3) * 8;
+  float2 *cout = a.cout + (int64_t)blockIdx.y * a.M;
+  const float2 *fw = a.fw + (int64_t)blockIdx.y * a.nftot;
+
+  const int r = lane >> 3, q = lane & 7;
+  const int xa = x0 - C::H, ya = y0 - C::H;
+  const int nf0 = a.nf[0], nf1 = a.nf[1];
+  float2 val[S][CX];
+#pragma unroll
+  for (int s = 0; s < S; s++) {
+    const int gy = wrap_once(ya + 4 * s + r, nf1);
+#pragma unroll
+    for (int c = 0; c < CX; c++) val[s][c] = __ldg(fw + (int64_t)gy * nf0 + wrap_once(xa + CX * q + c, nf0));
+  }
+
+  Rt2Row pr;
+  const float *myx = rows + C::KXO + 2 * CX * q;
+  const float *myy = rows + C::KYO + 2 * S * r;
+  const PtRec<float> *recp = a.rec + first + lane;
+  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
+  for (int b0 = 0; b0 < cnt; b0 += C::PB) {
+    const int nb = min(C::PB, cnt - b0);
+    const float4 recB = b0 + C::PB + lane < cnt ? ld_stream4(recp + b0 + C::PB) : zrec;
+    const int orig = __float_as_int(recA.w);
+    float2 mine = make_float2(0.f, 0.f);
+    __syncwarp();
+    if (lane < nb) rt2_weights<NS>(tab, recA, make_float2(1.f, 1.f), xa, ya, rows + lane * C::ROW);
+    __syncwarp();
+    recA = recB;
+    pr.load_x(myx, 0);
+    pr.load_y(myy, 0, 0);
+    pr.load_y(myy, 0, 1);
+    int ro = 0;
+    for (int t = 0; t < nb; t++) {
+      const int ron = t + 1 < nb ? ro + C::ROW : ro;
+      const float2 k0 = pr.cxp(0), k1 = pr.cxp(1);  // (kx, kx) of this lane's two cells
+      pr.load_x(myx, ron);
+      float2 res = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int s = 2 * i; s < 2 * i + 2; s++) {
+          const float2 t0 = fma2(val[s][1], k1, mul2(val[s][0], k0));
+          res = fma2(t0, pr.kyp(s), res);
+        }
+        pr.load_y(myy, ron, i);
+      }
+      res_w[(t & 7) * 33] = res;
+      if ((t & 7) == 7 || t == nb - 1) {
+        __syncwarp();
+        const int part = lane >> 3;
+        float2 s0 = res_r[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) s0 = add2(s0, res_r[j]);
+        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 8);
+        s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 8);
+        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);
+        s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);
+        if (part == (t >> 3)) mine = s0;
+        __syncwarp();
+      }
+      ro = ron;
+    }
+    if (lane < nb) {
+      float2 o = mine;
+      if (a.scale) {
+        const float2 sc = __ldg(a.scale + orig);
+        o = make_float2(o.x * sc.x - o.y * sc.y, o.x * sc.y + o.y * sc.x);
+      }
+      cout[orig] = o;
+    }
+  }
+}
+
+}  // namespace b2n

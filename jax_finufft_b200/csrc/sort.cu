@@ -174,6 +174,7 @@ __device__ __forceinline__ int div_bin(const SortGeom &g, int d, int u) {
 __device__ __forceinline__ int swr_key(const SortGeom &g, float &xr, float &yr, float &zr) {
   const int ux = swr_anchor(xr, g.swr_ns, g.nf[0]);
   const int uy = swr_anchor(yr, g.swr_ns, g.nf[1]);
+  if (g.dim == 2) return div_bin(g, 0, ux) + g.nbin[0] * div_bin(g, 1, uy);  // register-tile kernels: no sub-key
   const int uz = swr_anchor(zr, g.swr_ns, g.nf[2]);
   const int bz = div_bin(g, 2, uz);
   const int b = div_bin(g, 0, ux) + g.nbin[0] * (div_bin(g, 1, uy) + g.nbin[1] * bz);
@@ -485,7 +486,11 @@ __global__ void __launch_bounds__(PA_T) k_place_agg(SortGeom g, int64_t M, const
     if (i < M) {
       r = load(i);
       v = slot[sl];
-      if (v == 0xffffffffu) key = point_key(g, r.x, r.y, r.z);
+      // RAW records are folded afresh: point_key also applies the anchor's periodic shift to them
+      if (RAW || v == 0xffffffffu) {
+        const int k = point_key(g, r.x, r.y, r.z);
+        if (v == 0xffffffffu) key = k;
+      }
     }
     // records whose key found no table entry: one global atomic per distinct key per warp
     const unsigned direct = __ballot_sync(0xffffffffu, i < M && v == 0xffffffffu);
@@ -577,7 +582,7 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   for (int d = 0; d < 3; d++)
     g.magic[d] = g.bin[d] > 1 ? (unsigned)(((1ull << 32) + g.bin[d] - 1) / g.bin[d]) : 0u;
   g.nsub = ps.nsub = (p.method == 3 && p.dim == 3) ? p.bin[2] : 1;
-  g.swr_ns = (p.method == 3 && p.dim == 3) ? p.ns : 0;
+  g.swr_ns = p.method == 3 ? p.ns : 0;
   const int nblk = (int)std::min<int64_t>(std::max<int64_t>(cdiv(M, 256), 1), 148 * 16);
   ps.sorted = p.opts.gpu_sort != 0 || p.method != 1;
   if (!ps.sorted) {

@@ -1,5 +1,5 @@
 // swr.cu -- ns dispatch + launch of the sliding-window register kernels (3-D, float, ns <= 8).
-#include "swr_kernels.cuh"
+#include "rt2_kernels.cuh"
 
 namespace b2n {
 
@@ -12,8 +12,16 @@ template <int NS> static void swr_bins_ns(int ns, int *bin) {
   }
   if constexpr (NS < 8) swr_bins_ns<NS + 1>(ns, bin);
 }
-// bins (in anchor cells) of the sliding-window kernels for kernel width ns
-void swr_bins(int ns, int *bin) { swr_bins_ns<2>(ns, bin); }
+// bins (in anchor cells) of the register kernels for kernel width ns: sliding window (3-D) or
+// register tile (2-D, Rt2Cfg: (17 - ns)^2)
+void swr_bins(int dim, int ns, int *bin) {
+  if (dim == 2) {
+    bin[0] = bin[1] = 17 - ns;
+    bin[2] = 1;
+    return;
+  }
+  swr_bins_ns<2>(ns, bin);
+}
 
 static void swr_fill(Plan<float> &p, SwrArgs &a) {
   a.rec = p.pts.rec;
@@ -61,6 +69,35 @@ template <> struct SwrDispatch<9> {
   static int interp(Plan<float> &, const SwrArgs &, int) { return B2N_ERR_METHOD_NOTVALID; }
 };
 
+template <int NS> struct Rt2Dispatch {
+  static int spread(Plan<float> &p, const SwrArgs &a, int ntr) {
+    if (p.ns == NS) {
+      using C = Rt2Cfg<NS>;
+      dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
+      B2N_CUDA_OK(cudaFuncSetAttribute(k_rt2_spread<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::spread_smem()));
+      k_rt2_spread<NS><<<grid, 32 * C::WARPS, C::spread_smem(), p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
+      B2N_LAUNCH_OK();
+      return 0;
+    }
+    return Rt2Dispatch<NS + 1>::spread(p, a, ntr);
+  }
+  static int interp(Plan<float> &p, const SwrArgs &a, int ntr) {
+    if (p.ns == NS) {
+      using C = Rt2Cfg<NS>;
+      dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
+      B2N_CUDA_OK(cudaFuncSetAttribute(k_rt2_interp<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::interp_smem()));
+      k_rt2_interp<NS><<<grid, 32 * C::WARPS, C::interp_smem(), p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
+      B2N_LAUNCH_OK();
+      return 0;
+    }
+    return Rt2Dispatch<NS + 1>::interp(p, a, ntr);
+  }
+};
+template <> struct Rt2Dispatch<9> {
+  static int spread(Plan<float> &, const SwrArgs &, int) { return B2N_ERR_METHOD_NOTVALID; }
+  static int interp(Plan<float> &, const SwrArgs &, int) { return B2N_ERR_METHOD_NOTVALID; }
+};
+
 int spread_swr(Plan<float> &p, const float2 *c, const float2 *prescale, float2 *fw, int ntr) {
   if (p.pts.M == 0 || p.pts.sp_cap == 0) return 0;
   SwrArgs a;
@@ -69,6 +106,7 @@ int spread_swr(Plan<float> &p, const float2 *c, const float2 *prescale, float2 *
   a.cout = nullptr;
   a.scale = prescale;
   a.fw = fw;
+  if (p.dim == 2) return Rt2Dispatch<2>::spread(p, a, ntr);
   return SwrDispatch<2>::spread(p, a, ntr);
 }
 
@@ -80,6 +118,7 @@ int interp_swr(Plan<float> &p, float2 *c, const float2 *postscale, const float2 
   a.cout = c;
   a.scale = postscale;
   a.fw = const_cast<float2 *>(fw);
+  if (p.dim == 2) return Rt2Dispatch<2>::interp(p, a, ntr);
   return SwrDispatch<2>::interp(p, a, ntr);
 }
 

@@ -190,6 +190,31 @@ def test_binsort_contract_vs_oracle(method, dist):
         assert (d[same_bin] >= 0).all()
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_clustered_at_the_periodic_seam(dim):
+    """All points in a box 8 fine cells wide that STRADDLES x = +pi (the seam of the periodic grid):
+    the sort takes its clustered path (hot-key table + aggregated placement, also with the records
+    folded afresh because M is small), and the register kernels' anchor cells wrap."""
+    import jax_finufft_b200 as J
+
+    rng = np.random.default_rng(5)
+    nm = (40, 36, 30)[:dim]
+    M = 60000
+    pts = []
+    for d in range(dim):
+        h = 2 * np.pi / (2 * nm[d])
+        x = np.pi + rng.uniform(-4 * h, 4 * h, M)          # outside [-pi, pi) on purpose: folded by the library
+        pts.append(x.astype(np.float32))
+    c = (rng.uniform(-1, 1, M) + 1j * rng.uniform(-1, 1, M)).astype(np.complex64)
+    f = J.nufft1(nm[::-1], T(c), *[T(x) for x in pts[::-1]], eps=1e-6, iflag=1).cpu().numpy()
+    fo = oracle.nufft1(nm, c, *[x.astype(np.float64) for x in pts], eps=1e-6, iflag=1, prec=1)
+    assert oracle.relerr(f, fo) < 2e-5
+    fk = (rng.uniform(-1, 1, nm[::-1]) + 1j * rng.uniform(-1, 1, nm[::-1])).astype(np.complex64)
+    c2 = J.nufft2(T(fk), *[T(x) for x in pts[::-1]], eps=1e-6, iflag=-1).cpu().numpy()
+    co = oracle.nufft2(fk, *[x.astype(np.float64) for x in pts], eps=1e-6, iflag=-1, prec=1)
+    assert oracle.relerr(c2, co) < 2e-5
+
+
 def test_edge_cases_empty_single_far_and_clustered():
     from jax_finufft_b200.plan import Plan
 
