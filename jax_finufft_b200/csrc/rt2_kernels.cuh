@@ -12,10 +12,13 @@
 //     accumulators per lane, all indices literals;
 //   * per batch of 32 points lane t evaluates the two kernel vectors of point t (FFMA2 Horner)
 //     and parks them in warp-private shared memory as the inner loop consumes them: strength *
-//     x-weight pairs per window column (zero outside the stencil), y weights duplicated (w, w) in
+//     x-weight pairs per window column (zero outside the stencil), y weights in
 //     [row mod 4][row / 4] order (zero outside);
-//   * per point the warp issues 3 LDS.128 + 8 FFMA2 (spread) -- cells outside the point's stencil
-//     multiply by zero -- with the same rolling reloads as the 3-D kernel;
+//   * per point the warp issues 2 LDS.128 + 8 FFMA2 (spread) -- cells outside the point's stencil
+//     multiply by zero -- with the same rolling reloads as the 3-D kernel.  The y weights are NOT
+//     stored as (w, w) pairs: an LDS.128 costs four shared-memory wavefronts per warp whatever
+//     it broadcasts, the first version (3 LDS.128 per point) ran the shared-memory pipe at 90 %
+//     (profiles/r01e_rt2_*), and the pairs FFMA2 needs are made with register moves instead;
 //   * the tile is added to the fine grid ONCE per subproblem with red.global.add.v2.f32.
 // The tile kernels they replace (tile_kernels.cuh) do an LDS.128 + STS.128 read-modify-write of
 // shared memory per touched row segment; measured 1.28 ms per 1e7-point transform at C4 (2-D
@@ -37,8 +40,8 @@ template <int NS> struct Rt2Cfg {
   static constexpr int PB = 32;
   static constexpr int NP = (NS + 1) / 2;
   static constexpr int KXO = 0;                        // WX pairs: spread (c.re kx, c.im kx); interp (kx, kx)
-  static constexpr int KYO = 2 * WX;                   // [r = row & 3][s = row >> 2] pairs (ky, ky)
-  static constexpr int ROW0 = KYO + 2 * WY;            // 64 floats
+  static constexpr int KYO = 2 * WX;                   // ky[r = row & 3][s = row >> 2]
+  static constexpr int ROW0 = KYO + WY;                // 48 floats
   static constexpr int ROW = ROW0 + 4;                 // stride / 4 odd
   static constexpr int WARPS = 4;
   static constexpr size_t spread_smem() { return (size_t)WARPS * PB * ROW * sizeof(float); }
@@ -96,26 +99,25 @@ __device__ __forceinline__ void rt2_weights(const HornerTable<float> &tab, const
   {
     int yl = isy - ya;
     yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
-    float2 *dst = reinterpret_cast<float2 *>(row + C::KYO);
+    float *dst = row + C::KYO;
 #pragma unroll
     for (int j = 0; j < NS; j++) {
       const int iy = yl + j;
-      dst[C::S * (iy & 3) + (iy >> 2)] = make_float2(ky[j], ky[j]);
+      dst[C::S * (iy & 3) + (iy >> 2)] = ky[j];
     }
   }
 }
 
-// this lane's share of one point's row: x pairs of its two cells, (ky, ky) of its four rows
+// this lane's share of one point's row: x pairs of its two cells, ky of its four rows
 struct Rt2Row {
-  float4 cx;      // pairs of cells 2q, 2q+1
-  float4 ky[2];   // pairs of rows r, r+4 | r+8, r+12
+  float4 cx;  // pairs of cells 2q, 2q+1
+  float4 ky;  // rows r, r+4, r+8, r+12
   __device__ __forceinline__ void load_x(const float *myx, int ro) { cx = *reinterpret_cast<const float4 *>(myx + ro); }
-  __device__ __forceinline__ void load_y(const float *myy, int ro, int i) {
-    ky[i] = *reinterpret_cast<const float4 *>(myy + ro + 4 * i);
-  }
+  __device__ __forceinline__ void load_y(const float *myy, int ro) { ky = *reinterpret_cast<const float4 *>(myy + ro); }
   __device__ __forceinline__ float2 cxp(int c) const { return c ? make_float2(cx.z, cx.w) : make_float2(cx.x, cx.y); }
   __device__ __forceinline__ float2 kyp(int s) const {
-    return (s & 1) ? make_float2(ky[s >> 1].z, ky[s >> 1].w) : make_float2(ky[s >> 1].x, ky[s >> 1].y);
+    const float k = s == 0 ? ky.x : (s == 1 ? ky.y : (s == 2 ? ky.z : ky.w));
+    return make_float2(k, k);
   }
 };
 
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
 
   Rt2Row pr;
   const float *myx = rows + C::KXO + 2 * CX * q;
-  const float *myy = rows + C::KYO + 2 * S * r;
+  const float *myy = rows + C::KYO + S * r;
   const PtRec<float> *recp = a.rec + first + lane;
   const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
   auto ldc = [&](const float4 &rc, float2 &sc) {
@@ -174,22 +176,21 @@ __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
     cA = cB;
     sA = sB;
     pr.load_x(myx, 0);
-    pr.load_y(myy, 0, 0);
-    pr.load_y(myy, 0, 1);
+    pr.load_y(myy, 0);
     int ro = 0;
+#pragma unroll 2
     for (int t = 0; t < nb; t++) {
       const int ron = t + 1 < nb ? ro + C::ROW : ro;
       const float2 c0 = pr.cxp(0), c1 = pr.cxp(1);
+      float2 k[S];
+#pragma unroll
+      for (int s = 0; s < S; s++) k[s] = pr.kyp(s);
       pr.load_x(myx, ron);
+      pr.load_y(myy, ron);
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
-#pragma unroll
-        for (int s = 2 * i; s < 2 * i + 2; s++) {
-          const float2 k = pr.kyp(s);
-          acc[s][0] = fma2(c0, k, acc[s][0]);
-          acc[s][1] = fma2(c1, k, acc[s][1]);
-        }
-        pr.load_y(myy, ron, i);
+      for (int s = 0; s < S; s++) {
+        acc[s][0] = fma2(c0, k[s], acc[s][0]);
+        acc[s][1] = fma2(c1, k[s], acc[s][1]);
       }
       ro = ron;
     }
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
 
   Rt2Row pr;
   const float *myx = rows + C::KXO + 2 * CX * q;
-  const float *myy = rows + C::KYO + 2 * S * r;
+  const float *myy = rows + C::KYO + S * r;
   const PtRec<float> *recp = a.rec + first + lane;
   const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
@@ -250,22 +251,22 @@ __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
     __syncwarp();
     recA = recB;
     pr.load_x(myx, 0);
-    pr.load_y(myy, 0, 0);
-    pr.load_y(myy, 0, 1);
+    pr.load_y(myy, 0);
     int ro = 0;
+#pragma unroll 2
     for (int t = 0; t < nb; t++) {
       const int ron = t + 1 < nb ? ro + C::ROW : ro;
       const float2 k0 = pr.cxp(0), k1 = pr.cxp(1);  // (kx, kx) of this lane's two cells
+      float2 k[S];
+#pragma unroll
+      for (int s = 0; s < S; s++) k[s] = pr.kyp(s);
       pr.load_x(myx, ron);
+      pr.load_y(myy, ron);
       float2 res = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
-#pragma unroll
-        for (int s = 2 * i; s < 2 * i + 2; s++) {
-          const float2 t0 = fma2(val[s][1], k1, mul2(val[s][0], k0));
-          res = fma2(t0, pr.kyp(s), res);
-        }
-        pr.load_y(myy, ron, i);
+      for (int s = 0; s < S; s++) {
+        const float2 t0 = fma2(val[s][1], k1, mul2(val[s][0], k0));
+        res = fma2(t0, k[s], res);
       }
       res_w[(t & 7) * 33] = res;
       if ((t & 7) == 7 || t == nb - 1) {
