@@ -68,9 +68,9 @@ template <int NS> struct SwrCfg {
   // per-point shared-memory row, in floats
   static constexpr int KXO = 0;              // WX pairs: spread (c.re*kx, c.im*kx); interp (kx, kx)
   static constexpr int KYO = 2 * WX;         // ky[row & 3][row >> 2], 4 x 4
-  static constexpr int KZO = KYO + 16;       // D pairs (kz, kz), plane order, then META
-  static constexpr int KZW = (2 * D + 2 + 3) & ~3;
-  static constexpr int MTO = KZO + KZW - 2;  // META = {first plane of the point's window, unused}
+  static constexpr int KZO = KYO + 16;       // D z weights in plane order (FFMA2 broadcasts a scalar operand), META last
+  static constexpr int KZW = (D + 1 + 3) & ~3;
+  static constexpr int MTO = KZO + KZW - 1;  // META = first plane of the point's window
   static constexpr int ROW0 = KZO + KZW;
   // stride/4 odd: lane-strided 16-byte accesses of 8 consecutive lanes hit 8 distinct bank groups
   static constexpr int ROW = (ROW0 / 4) % 2 == 1 ? ROW0 : ROW0 + 4;
@@ -197,13 +197,13 @@ __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const
     }
   }
   {
-    float *dst = row + C::KZO;
+    float kzm[C::KZW];
 #pragma unroll
-    for (int j = 0; j + 1 < NS; j += 2)
-      *reinterpret_cast<float4 *>(dst + 2 * j) = make_float4(kz[j], kz[j], kz[j + 1], kz[j + 1]);
-    if constexpr (NS % 2 == 1)
-      *reinterpret_cast<float2 *>(dst + 2 * (NS - 1)) = make_float2(kz[NS - 1], kz[NS - 1]);
-    *reinterpret_cast<int2 *>(row + C::MTO) = make_int2(isz, 0);
+    for (int j = 0; j < C::KZW; j++) kzm[j] = j < NS ? kz[j] : 0.f;
+    kzm[C::KZW - 1] = __int_as_float(isz);
+#pragma unroll
+    for (int i = 0; i < C::KZW / 4; i++)
+      *reinterpret_cast<float4 *>(row + C::KZO + 4 * i) = make_float4(kzm[4 * i], kzm[4 * i + 1], kzm[4 * i + 2], kzm[4 * i + 3]);
   }
 }
 
@@ -215,7 +215,7 @@ __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const
 template <int NS> struct SwrRow {
   using C = SwrCfg<NS>;
   static constexpr int NV = C::KZW / 4;
-  float4 kv[NV];       // kz pairs 2i, 2i+1 (the last one ends with META)
+  float4 kv[NV];       // kz 4i .. 4i+3 (the last one ends with META)
   float2 cx[C::CX];
   float4 ky;
   __device__ __forceinline__ void load_xy(const float *myx, const float *myy, int ro) {
@@ -231,11 +231,16 @@ template <int NS> struct SwrRow {
   __device__ __forceinline__ void load_kv(const float *rows, int ro, int i) {
     kv[i] = *reinterpret_cast<const float4 *>(rows + ro + C::KZO + 4 * i);
   }
-  __device__ __forceinline__ float2 kz(int j) const {
-    return (j & 1) ? make_float2(kv[j / 2].z, kv[j / 2].w) : make_float2(kv[j / 2].x, kv[j / 2].y);
+  __device__ __forceinline__ float2 kz(int j) const {  // (kz, kz): a scalar-broadcast FFMA2 operand
+    const float4 v = kv[j / 4];
+    const float k = (j & 3) == 0 ? v.x : ((j & 3) == 1 ? v.y : ((j & 3) == 2 ? v.z : v.w));
+    return make_float2(k, k);
   }
-  __device__ __forceinline__ int zw() const { return __float_as_int(kv[NV - 1].z); }
-  __device__ __forceinline__ float kyv(int s) const { return s == 0 ? ky.x : (s == 1 ? ky.y : (s == 2 ? ky.z : ky.w)); }
+  __device__ __forceinline__ int zw() const { return __float_as_int(kv[NV - 1].w); }
+  __device__ __forceinline__ float2 kyv(int s) const {
+    const float k = s == 0 ? ky.x : (s == 1 ? ky.y : (s == 2 ? ky.z : ky.w));
+    return make_float2(k, k);
+  }
 };
 
 // ==================================================================================== SPREAD
@@ -298,12 +303,12 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
 #pragma unroll
     for (int s = 0; s < S; s++)
 #pragma unroll
-      for (int c = 0; c < CX; c++) wv[s][c] = make_float2(pr.cx[c].x * pr.kyv(s), pr.cx[c].y * pr.kyv(s));
+      for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
     pr.load_xy(myx, myy, ron);
 #pragma unroll
     for (int i = 0; i < SwrRow<NS>::NV; i++) {
 #pragma unroll
-      for (int j = 2 * i; j < 2 * i + 2; j++) {
+      for (int j = 4 * i; j < 4 * i + 4; j++) {
         if (j < D) {
           const float2 kzj = pr.kz(j);
 #pragma unroll
@@ -482,13 +487,13 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
 #pragma unroll
     for (int s = 0; s < S; s++)
 #pragma unroll
-      for (int c = 0; c < CX; c++) wv[s][c] = make_float2(pr.cx[c].x * pr.kyv(s), pr.cx[c].y * pr.kyv(s));
+      for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
     pr.load_xy(myx, myy, ron);
     float2 part[S][CX];
 #pragma unroll
     for (int i = 0; i < SwrRow<NS>::NV; i++) {
 #pragma unroll
-      for (int j = 2 * i; j < 2 * i + 2; j++) {
+      for (int j = 4 * i; j < 4 * i + 4; j++) {
         if (j < D) {
           const float2 kzj = pr.kz(j);
 #pragma unroll
