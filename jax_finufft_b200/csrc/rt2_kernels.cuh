@@ -94,7 +94,7 @@ __device__ __forceinline__ void rt2_weights(const HornerTable<float> &tab, const
     xl = xl < 0 ? 0 : (xl > C::WX - NS ? C::WX - NS : xl);
     float2 *dst = reinterpret_cast<float2 *>(row + C::KXO) + xl;
 #pragma unroll
-    for (int j = 0; j < NS; j++) dst[j] = make_float2(cv.x * kx[j], cv.y * kx[j]);
+    for (int j = 0; j < NS; j++) dst[j] = mul2(cv, make_float2(kx[j], kx[j]));
   }
   {
     int yl = isy - ya;
@@ -203,6 +203,165 @@ __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
     for (int c = 0; c < CX; c++) {
       const int gx = wrap_once(xa + CX * q + c, nf0);
       if (acc[s][c].x != 0.f || acc[s][c].y != 0.f) red_add(fw + (int64_t)gy * nf0 + gx, acc[s][c]);
+    }
+  }
+}
+
+// ==================================================================================== SPREAD, stacked
+// NT transforms that share the points (jax-finufft's vmap stacking, n_transf > 1) in ONE pass of
+// the warp: the kernel vectors are evaluated and loaded once per point, only the strength differs.
+// Row layout: kx[16] | ky[16] ([r][s]) | NT strengths.  Per point: LDS.64 (kx of this lane's two
+// cells) + LDS.128 (ky of its four rows) + NT/2 LDS.128 (strengths, broadcast), then per transform
+// 2 FMUL2 + 8 FFMA2.  32 complex accumulators per lane at NT = 4.
+template <int NS, int NT> struct Rt2NtCfg {
+  using B = Rt2Cfg<NS>;
+  static constexpr int KXO = 0, KYO = B::WX, CSO = B::WX + B::WY;
+  static constexpr int ROW0 = CSO + 2 * NT;                      // 40 floats at NT = 4
+  static constexpr int ROW = (ROW0 / 4) % 2 == 1 ? ROW0 : ROW0 + 4;
+  static constexpr size_t smem() { return (size_t)B::WARPS * B::PB * ROW * sizeof(float); }
+};
+
+template <int NS, int NT>
+__global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
+    k_rt2_spread_nt(const SwrArgs a, const __grid_constant__ HornerTable<float> tab, int ntr) {
+  using C = Rt2Cfg<NS>;
+  using R = Rt2NtCfg<NS, NT>;
+  constexpr int S = C::S, CX = C::CX, NP = C::NP;
+  static_assert(NT % 2 == 0, "strengths are loaded two at a time");
+  extern __shared__ __align__(16) float swr_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int first, cnt, x0, y0;
+  if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
+  float *rows = swr_smem + w * (C::PB * R::ROW);
+  const int t0 = blockIdx.y * NT;                       // first transform of this pass
+  const int nt = min(NT, ntr - t0);
+  const float2 *cin = a.cin + (int64_t)t0 * a.M;
+  float2 *fw = a.fw + (int64_t)t0 * a.nftot;
+
+  const int r = lane >> 3, q = lane & 7;
+  const int xa = x0 - C::H, ya = y0 - C::H;
+  const int nf0 = a.nf[0], nf1 = a.nf[1];
+
+  float2 acc[NT][S][CX];
+#pragma unroll
+  for (int t = 0; t < NT; t++)
+#pragma unroll
+    for (int s = 0; s < S; s++)
+#pragma unroll
+      for (int c = 0; c < CX; c++) acc[t][s][c] = make_float2(0.f, 0.f);
+
+  const float *myx = rows + R::KXO + CX * q;
+  const float *myy = rows + R::KYO + S * r;
+  const PtRec<float> *recp = a.rec + first + lane;
+  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float2 zero2 = make_float2(0.f, 0.f);
+  // strengths of the point of record rc for the nt transforms of this pass
+  auto ldc = [&](const float4 &rc, float2 (&cv)[NT]) {
+    const int o = __float_as_int(rc.w);
+#pragma unroll
+    for (int t = 0; t < NT; t++) cv[t] = t < nt ? ld_stream2(cin + (int64_t)t * a.M + o) : zero2;
+  };
+  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
+  float4 recB = lane + C::PB < cnt ? ld_stream4(recp + C::PB) : zrec;
+  float2 cA[NT], cB[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) cA[t] = cB[t] = zero2;
+  if (lane < cnt) ldc(recA, cA);
+  for (int b0 = 0; b0 < cnt; b0 += C::PB) {
+    const int nb = min(C::PB, cnt - b0);
+    const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
+    if (b0 + C::PB + lane < cnt) ldc(recB, cB);
+    __syncwarp();
+    if (lane < nb) {  // kernel vectors of point b0 + lane, once for all transforms
+      float *row = rows + lane * R::ROW;
+      const float px = recA.x, py = recA.y;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < R::CSO / 4; i++) reinterpret_cast<float4 *>(row)[i] = z4;
+      const int isx = window_start(px, NS), isy = window_start(py, NS);
+      float kx[2 * NP], ky[2 * NP];
+      if (!tab.direct) {
+        const float zx = fmaf(2.f, float(isx) - px, float(NS - 1));
+        const float zy = fmaf(2.f, float(isy) - py, float(NS - 1));
+        const float2 zx2 = make_float2(zx, zx), zy2 = make_float2(zy, zy);
+        float2 ax[NP], ay[NP];
+#pragma unroll
+        for (int j = 0; j < NP; j++) ax[j] = ay[j] = make_float2(tab.c[0][2 * j], tab.c[0][2 * j + 1]);
+        for (int k = 1; k < tab.ncoef; k++) {
+#pragma unroll
+          for (int j = 0; j < NP; j++) {
+            const float2 cj = make_float2(tab.c[k][2 * j], tab.c[k][2 * j + 1]);
+            ax[j] = fma2(ax[j], zx2, cj);
+            ay[j] = fma2(ay[j], zy2, cj);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+          kx[2 * j] = ax[j].x; kx[2 * j + 1] = ax[j].y;
+          ky[2 * j] = ay[j].x; ky[2 * j + 1] = ay[j].y;
+        }
+      } else {
+        float tx[NS], ty[NS];
+        eval_kernel<float, NS>(tx, float(isx) - px, tab);
+        eval_kernel<float, NS>(ty, float(isy) - py, tab);
+#pragma unroll
+        for (int j = 0; j < NS; j++) { kx[j] = tx[j]; ky[j] = ty[j]; }
+      }
+      int xl = isx - xa;
+      xl = xl < 0 ? 0 : (xl > C::WX - NS ? C::WX - NS : xl);
+      int yl = isy - ya;
+      yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
+#pragma unroll
+      for (int j = 0; j < NS; j++) {
+        row[R::KXO + xl + j] = kx[j];
+        const int iy = yl + j;
+        row[R::KYO + S * (iy & 3) + (iy >> 2)] = ky[j];
+      }
+#pragma unroll
+      for (int t = 0; t < NT; t += 2)
+        *reinterpret_cast<float4 *>(row + R::CSO + 2 * t) = make_float4(cA[t].x, cA[t].y, cA[t + 1].x, cA[t + 1].y);
+    }
+    __syncwarp();
+    recA = recB;
+    recB = recC;
+#pragma unroll
+    for (int t = 0; t < NT; t++) cA[t] = cB[t];
+    int ro = 0;
+#pragma unroll 2
+    for (int p = 0; p < nb; p++) {
+      const float2 kx2 = *reinterpret_cast<const float2 *>(myx + ro);
+      const float4 ky4 = *reinterpret_cast<const float4 *>(myy + ro);
+      const float kyv[4] = {ky4.x, ky4.y, ky4.z, ky4.w};
+#pragma unroll
+      for (int t = 0; t < NT; t += 2) {
+        const float4 c2 = *reinterpret_cast<const float4 *>(rows + ro + R::CSO + 2 * t);
+        const float2 ct[2] = {make_float2(c2.x, c2.y), make_float2(c2.z, c2.w)};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          const float2 w0 = mul2(ct[u], make_float2(kx2.x, kx2.x)), w1 = mul2(ct[u], make_float2(kx2.y, kx2.y));
+#pragma unroll
+          for (int s = 0; s < S; s++) {
+            const float2 k = make_float2(kyv[s], kyv[s]);
+            acc[t + u][s][0] = fma2(w0, k, acc[t + u][s][0]);
+            acc[t + u][s][1] = fma2(w1, k, acc[t + u][s][1]);
+          }
+        }
+      }
+      ro += R::ROW;
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    if (t >= nt) break;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      const int gy = wrap_once(ya + 4 * s + r, nf1);
+#pragma unroll
+      for (int c = 0; c < CX; c++) {
+        const int gx = wrap_once(xa + CX * q + c, nf0);
+        if (acc[t][s][c].x != 0.f || acc[t][s][c].y != 0.f)
+          red_add(fw + (int64_t)t * a.nftot + (int64_t)gy * nf0 + gx, acc[t][s][c]);
+      }
     }
   }
 }

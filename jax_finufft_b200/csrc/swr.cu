@@ -73,6 +73,15 @@ template <int NS> struct Rt2Dispatch {
   static int spread(Plan<float> &p, const SwrArgs &a, int ntr) {
     if (p.ns == NS) {
       using C = Rt2Cfg<NS>;
+      if (ntr > 1 && !a.scale) {  // stacked transforms sharing the points: RT2_NT of them per warp pass
+        constexpr int NT = 4;
+        using R = Rt2NtCfg<NS, NT>;
+        dim3 gridn((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)cdiv(ntr, NT));
+        B2N_CUDA_OK(cudaFuncSetAttribute(k_rt2_spread_nt<NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::smem()));
+        k_rt2_spread_nt<NS, NT><<<gridn, 32 * C::WARPS, R::smem(), p.stream>>>(a, p.tab, ntr);  B2N_LAUNCHED(1);
+        B2N_LAUNCH_OK();
+        return 0;
+      }
       dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
       B2N_CUDA_OK(cudaFuncSetAttribute(k_rt2_spread<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::spread_smem()));
       k_rt2_spread<NS><<<grid, 32 * C::WARPS, C::spread_smem(), p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);

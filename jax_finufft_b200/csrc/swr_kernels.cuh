@@ -185,7 +185,7 @@ __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const
     xl = xl < 0 ? 0 : (xl > C::WX - NS ? C::WX - NS : xl);
     float2 *dst = reinterpret_cast<float2 *>(row + C::KXO) + xl;
 #pragma unroll
-    for (int j = 0; j < NS; j++) dst[j] = make_float2(cv.x * kx[j], cv.y * kx[j]);
+    for (int j = 0; j < NS; j++) dst[j] = mul2(cv, make_float2(kx[j], kx[j]));
   }
   {
     int yl = isy - ya;
