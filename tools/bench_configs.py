@@ -47,6 +47,22 @@ def stages(p, setpts, execute, K=3):
     return {k: round(v / K, 4) for k, v in p.timings().items()}
 
 
+def c1():
+    """1-D type 1, M=1e6 random points, N=1e6 modes, eps=1e-6, complex128 (BASELINE configs[0], the
+    reference's CPU-runnable case; here on the GPU in double precision)."""
+    g = torch.Generator(device=dev).manual_seed(123)
+    M, N = 10 ** 6, 10 ** 6
+    x = (torch.rand(M, device=dev, generator=g, dtype=torch.float64) * 2 * np.pi)
+    c = torch.complex(torch.randn(M, device=dev, generator=g, dtype=torch.float64),
+                      torch.randn(M, device=dev, generator=g, dtype=torch.float64))
+    ms = timed(lambda: J.nufft1((N,), c, x, eps=1e-6, iflag=1))
+    p = Plan(1, (N,), eps=1e-6, isign=1, dtype="complex128", debug=1)
+    st = stages(p, lambda: p.setpts(x), lambda: p.execute(c[None]))
+    p.destroy()
+    return {"config": "C1 1-D type 1 M=1e6 N=1e6 eps=1e-6 c128", "ms_per_step": ms, "points_per_s": M / ms * 1e3,
+            "stages_ms": st}
+
+
 def c2():
     """2-D type 2, M=1e7, N=2048^2, eps=1e-5, complex64 (BASELINE configs[1])."""
     g = torch.Generator(device=dev).manual_seed(1)
@@ -85,7 +101,7 @@ def c5(grad=False):
     c = cplx(M, g)
     if not grad:
         ms = timed(lambda: J.nufft3(c, *x, *s, eps=1e-6, iflag=-1), K=3, W=2)
-        p = Plan(3, 3, eps=1e-6, isign=-1, debug=1)
+        p = Plan(3, 3, eps=1e-6, isign=-1, debug=1, upsampfac=2.0)  # jax-finufft default (options.py:66)
         st = stages(p, lambda: p.setpts(x[2], x[1], x[0], s[2], s[1], s[0]), lambda: p.execute(c[None]))
         p.destroy()
         return {"config": "C5 3-D type 3 M=1e7 -> N=1e7 (targets in [-64,64)^3) eps=1e-6 c64", "ms_per_step": ms,
@@ -107,9 +123,9 @@ def c5(grad=False):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c2", "c4", "c5", "c5grad"]
+    which = sys.argv[1:] or ["c1", "c2", "c4", "c5", "c5grad"]
     for wname in which:
-        fn = {"c2": c2, "c4": c4, "c5": c5, "c5grad": lambda: c5(True)}[wname]
+        fn = {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "c5grad": lambda: c5(True)}[wname]
         try:
             r = fn()
         except Exception as e:  # keep going: one config failing must not hide the others
