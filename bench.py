@@ -298,8 +298,14 @@ def main_ours(a):
                                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                                 "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel_ms": st[kern],
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                                "note": "3-D ns=7 spread/interp is FP32-pipe-bound (343 complex cell updates per point, kept in "
-                                        "registers), see DESIGN.md; HBM fraction reported as the contract asks"}
+                                "note": "3-D ns=7 spread/interp is FP32-pipe/issue-bound (343 complex cell updates per point, kept in "
+                                        "registers), see DESIGN.md 4.2; HBM fraction reported as the contract asks",
+                                # the binding unit: useful FMAs (2 * ns^3 per point) against 148 SMs x 128 FP32 lanes
+                                "fp32": {"useful_fma_per_point": 686,
+                                         "achieved_tfma_s": 686 * M / (st[kern] * 1e-3) / 1e12,
+                                         "peak_tfma_s": 148 * 128 * float((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6 / 1e12}}
+            fp = line["roofline"]["fp32"]
+            fp["frac"] = fp["achieved_tfma_s"] / fp["peak_tfma_s"]
             line["stages_ms"] = st
         barrier()
 

@@ -247,9 +247,13 @@ int Plan<T>::setpts(int64_t M, const void *x, const void *y, const void *z, int6
 // register window per subproblem, which only amortises on reasonably dense point sets.
 template <typename T> void Plan<T>::set_geometry(int64_t M) {
   static const char *force = getenv("B2N_FORCE_METHOD");
-  // dense enough to fill the bins: 3-D bins hold 2 x 6 x 64 anchor cells, 2-D bins (17 - ns)^2
+  static const double dens3 = getenv("B2N_SWR_DENSITY3") ? atof(getenv("B2N_SWR_DENSITY3")) : 0.05;
+  static const double dens2 = getenv("B2N_SWR_DENSITY2") ? atof(getenv("B2N_SWR_DENSITY2")) : 0.10;
+  // dense enough to fill the bins (3-D bins hold 2 x 6 x 64 anchor cells, 2-D bins (17 - ns)^2).
+  // Thresholds measured on B200: 3-D interp at 0.064 points per cell 1.24 ms (SWR) vs 2.82 ms (tile);
+  // 2-D at 0.12 points per cell 0.53 ms (RT2) vs 0.81 ms (tile)
   bool swr = swr_ok && nf[0] % 2 == 0 && nf[0] >= 32 && nf[1] >= 32 &&
-             (dim == 3 ? nf[2] >= 32 && (double)M >= 0.08 * (double)nftot : (double)M >= 0.25 * (double)nftot);
+             (dim == 3 ? nf[2] >= 32 && (double)M >= dens3 * (double)nftot : (double)M >= dens2 * (double)nftot);
   if (force && swr_ok) swr = force[0] == '3';
   if (swr) {
     method = 3;
@@ -420,7 +424,7 @@ template <typename T> int Plan<T>::exec_phase(int phase, void *cv, void *fkv) {
 template <typename T> bool Plan<T>::can_chunk(int64_t M, int *nchunk, int64_t *chunk) const {
   static const char *off = getenv("B2N_NO_CHUNK");
   if (off || type == 3 || ntransf != 1 || opts.gpu_spreadinterponly || M < (int64_t(1) << 23)) return false;
-  int64_t n = std::min<int64_t>(8, M / std::max<int64_t>(1, (int64_t)(0.09 * (double)nftot)));
+  int64_t n = std::min<int64_t>(8, M / std::max<int64_t>(1, (int64_t)(0.06 * (double)nftot)));
   if (n < 2) return false;
   int64_t ch = ((M + n - 1) / n + 31) & ~int64_t(31);  // keeps every chunk's arrays 128-byte aligned
   *chunk = ch;

@@ -45,7 +45,7 @@ template <int NS> struct Rt2Cfg {
   static constexpr int ROW = ROW0 + 4;                 // stride / 4 odd
   static constexpr int WARPS = 4;
   static constexpr size_t spread_smem() { return (size_t)WARPS * PB * ROW * sizeof(float); }
-  static constexpr size_t interp_warp_floats = PB * ROW + 2 * 8 * 33;
+  static constexpr size_t interp_warp_floats = PB * ROW + 2 * 16 * 33;
   static constexpr size_t interp_smem() { return (size_t)WARPS * interp_warp_floats * sizeof(float); }
   static_assert(BX >= 1 && BY >= 1, "window too small");
 };
@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
   if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
   float *rows = swr_smem + w * C::interp_warp_floats;
   float2 *RES = reinterpret_cast<float2 *>(rows + C::PB * C::ROW);
-  float2 *res_w = RES + lane;
-  const float2 *res_r = RES + (lane & 7) * 33 + (lane >> 3) * 8;
+  float2 *res_w = RES + lane;                                        // + (t & 15) * 33 per point
+  const float2 *res_r = RES + (lane & 15) * 33 + (lane >> 4) * 16;  // this lane's 16 terms of a half-batch sum
   float2 *cout = a.cout + (int64_t)blockIdx.y * a.M;
   const float2 *fw = a.fw + (int64_t)blockIdx.y * a.nftot;
 
@@ -411,37 +411,40 @@ __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
     recA = recB;
     pr.load_x(myx, 0);
     pr.load_y(myy, 0);
-    int ro = 0;
+    int ro = 0, t = 0;
+    for (int half = 0; half * 16 < nb; half++) {
+      const int tend = min(nb, 16 * half + 16);
+      float2 *rw = res_w;
 #pragma unroll 2
-    for (int t = 0; t < nb; t++) {
-      const int ron = t + 1 < nb ? ro + C::ROW : ro;
-      const float2 k0 = pr.cxp(0), k1 = pr.cxp(1);  // (kx, kx) of this lane's two cells
-      float2 k[S];
+      for (; t < tend; t++) {
+        const int ron = t + 1 < nb ? ro + C::ROW : ro;
+        const float2 k0 = pr.cxp(0), k1 = pr.cxp(1);  // (kx, kx) of this lane's two cells
+        float2 k[S];
 #pragma unroll
-      for (int s = 0; s < S; s++) k[s] = pr.kyp(s);
-      pr.load_x(myx, ron);
-      pr.load_y(myy, ron);
-      float2 res = make_float2(0.f, 0.f);
+        for (int s = 0; s < S; s++) k[s] = pr.kyp(s);
+        pr.load_x(myx, ron);
+        pr.load_y(myy, ron);
+        float2 res = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int s = 0; s < S; s++) {
-        const float2 t0 = fma2(val[s][1], k1, mul2(val[s][0], k0));
-        res = fma2(t0, k[s], res);
+        for (int s = 0; s < S; s++) {
+          const float2 t0 = fma2(val[s][1], k1, mul2(val[s][0], k0));
+          res = fma2(t0, k[s], res);
+        }
+        *rw = res;
+        rw += 33;
+        ro = ron;
       }
-      res_w[(t & 7) * 33] = res;
-      if ((t & 7) == 7 || t == nb - 1) {
-        __syncwarp();
-        const int part = lane >> 3;
+      // lane (row, part) sums half of row `row`; one butterfly step finishes it (swr_kernels.cuh)
+      __syncwarp();
+      {
         float2 s0 = res_r[0];
 #pragma unroll
-        for (int j = 1; j < 8; j++) s0 = add2(s0, res_r[j]);
-        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 8);
-        s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 8);
+        for (int j = 1; j < 16; j++) s0 = add2(s0, res_r[j]);
         s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);
         s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);
-        if (part == (t >> 3)) mine = s0;
-        __syncwarp();
+        if ((lane >> 4) == half) mine = s0;
       }
-      ro = ron;
+      __syncwarp();
     }
     if (lane < nb) {
       float2 o = mine;

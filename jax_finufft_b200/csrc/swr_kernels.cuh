@@ -413,12 +413,13 @@ sub_done:;
 }
 
 // ==================================================================================== INTERP
-// Per-warp shared memory: the weight rows + RES[8][33] float2 partial results of a group of 8
-// points (point t, lane j at [t & 7][j]; the odd row stride makes both the per-point store and
-// the per-group sums -- lane (row, part) adds columns part*8 .. part*8+7 of its row -- free of
-// bank conflicts with constant per-lane offsets).
+// Per-warp shared memory: the weight rows + RES[16][33] float2 partial results of half a batch
+// (point t, lane j at [t & 15][j]; the odd row stride makes both the per-point store and the
+// per-half sums -- lane (row, part) adds columns part*16 .. part*16+15 of its row -- free of bank
+// conflicts with constant per-lane offsets).  The half-batch boundary is treated like a batch
+// boundary of the phase chain, so the inner loop carries no "group full?" test.
 template <int NS> struct SwrInterpSmem {
-  static constexpr size_t warp_floats = SwrCfg<NS>::PB * SwrCfg<NS>::ROW + 2 * 8 * 33;  // multiple of 4 floats: rows stay 16-byte aligned
+  static constexpr size_t warp_floats = SwrCfg<NS>::PB * SwrCfg<NS>::ROW + 2 * 16 * 33;  // multiple of 4 floats: rows stay 16-byte aligned
   static constexpr size_t bytes() { return SwrCfg<NS>::WARPS * warp_floats * sizeof(float); }
 };
 
@@ -433,8 +434,8 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
   if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
   float *rows = swr_smem + w * SwrInterpSmem<NS>::warp_floats;
   float2 *RES = reinterpret_cast<float2 *>(rows + C::PB * C::ROW);
-  float2 *res_w = RES + lane;                                 // + (t & 7) * 33 per point
-  const float2 *res_r = RES + (lane & 7) * 33 + (lane >> 3) * 8;  // this lane's 8 terms of the group sum
+  float2 *res_w = RES + lane;                                        // + (t & 15) * 33 per point
+  const float2 *res_r = RES + (lane & 15) * 33 + (lane >> 4) * 16;  // this lane's 16 terms of a half-batch sum
   float2 *cout = a.cout + (int64_t)blockIdx.y * a.M;
 
   const int r = lane >> 3, q = lane & 7;
@@ -535,42 +536,32 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     for (int i = 0; i < SwrRow<NS>::NV; i++) pr.load_kv(rows, 0, i);
     int zw = pr.zw();
     bool fill = cur == SWR_EMPTY;
-  reenter:
-    if (fill) {  // first point, or a gap wider than the ring (or disorder): one shared copy
-      cur = zw;
-      refill(cur);
-      ph = 0;
-      fill = false;
-    }
-    for (;;) {
-      switch (ph) {
+    for (int half = 0; half * 16 < nb; half++) {
+      const int tend = min(nb, 16 * half + 16);
+      float2 *rw = res_w;
+    reenter:
+      if (fill) {  // first point, or a gap wider than the ring (or disorder): one shared copy
+        cur = zw;
+        refill(cur);
+        ph = 0;
+        fill = false;
+      }
+      for (;;) {
+        switch (ph) {
 #define SWR_INTERP_PHASE(PH)                                                                    \
   case PH:                                                                                      \
     if constexpr (PH < D) {                                                                     \
-      while (t < nb && zw == cur) {                                                             \
+      while (t < tend && zw == cur) {                                                           \
         const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
-        res_w[(t & 7) * 33] = point(std::integral_constant<int, PH>{}, ron);                    \
-        if ((t & 7) == 7 || t == nb - 1) {                                                      \
-          /* group of <= 8 points done: lane j sums quarter j>>3 of row j&7, two butterfly */   \
-          /* steps finish the row; point 8g + row lives in lane 8g + row, which keeps it */     \
-          __syncwarp();                                                                         \
-          const int part = lane >> 3;                                                           \
-          float2 s0 = res_r[0];                                                                 \
-          _Pragma("unroll") for (int j = 1; j < 8; j++) s0 = add2(s0, res_r[j]);                \
-          s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 8);                                        \
-          s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 8);                                        \
-          s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);                                       \
-          s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);                                       \
-          if (part == (t >> 3)) mine = s0;                                                      \
-          __syncwarp();                                                                         \
-        }                                                                                       \
+        *rw = point(std::integral_constant<int, PH>{}, ron);                                    \
+        rw += 33;                                                                               \
         t++;                                                                                    \
         ro = ron;                                                                               \
         zw = pr.zw();                                                                           \
       }                                                                                         \
-      if (t >= nb) {                                                                            \
+      if (t >= tend) {                                                                          \
         ph = PH;                                                                                \
-        goto batch_done;                                                                        \
+        goto half_done;                                                                         \
       }                                                                                         \
       if ((unsigned)(zw - cur) >= (unsigned)D) {                                                \
         fill = true;                                                                            \
@@ -582,20 +573,33 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
       cur++;                                                                                    \
       fetch(cur + D, pre);                                                                      \
     }
-        SWR_INTERP_PHASE(0)
-        SWR_INTERP_PHASE(1)
-        SWR_INTERP_PHASE(2)
-        SWR_INTERP_PHASE(3)
-        SWR_INTERP_PHASE(4)
-        SWR_INTERP_PHASE(5)
-        SWR_INTERP_PHASE(6)
-        SWR_INTERP_PHASE(7)
+          SWR_INTERP_PHASE(0)
+          SWR_INTERP_PHASE(1)
+          SWR_INTERP_PHASE(2)
+          SWR_INTERP_PHASE(3)
+          SWR_INTERP_PHASE(4)
+          SWR_INTERP_PHASE(5)
+          SWR_INTERP_PHASE(6)
+          SWR_INTERP_PHASE(7)
 #undef SWR_INTERP_PHASE
-        default: break;
+          default: break;
+        }
+        ph = 0;
       }
-      ph = 0;
+    half_done:
+      // lane (row, part) sums half of row `row`; one butterfly step finishes it.  Point
+      // 16 * half + row belongs to lane 16 * half + row = the lane with part == half.
+      __syncwarp();
+      {
+        float2 s0 = res_r[0];
+#pragma unroll
+        for (int j = 1; j < 16; j++) s0 = add2(s0, res_r[j]);
+        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);
+        s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);
+        if ((lane >> 4) == half) mine = s0;
+      }
+      __syncwarp();
     }
-  batch_done:
     if (lane < nb) {
       float2 o = mine;
       if (a.scale) {
