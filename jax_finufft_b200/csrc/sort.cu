@@ -135,10 +135,38 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_add(int32_t *__restrict__ out, 
     if (base + k < n) out[base + k] += add;
 }
 
+// small inputs (1-D plans, the per-bin subproblem counts of small grids): one block, one launch --
+// at M = 1e6 the sort is bound by launch gaps, not by bytes
+constexpr int SCAN_SMALL = 1024 * SCAN_E;
+__global__ void __launch_bounds__(1024) k_scan_small(const int32_t *__restrict__ in, int32_t *__restrict__ out, int n) {
+  __shared__ int sm[33];
+  const int base = threadIdx.x * SCAN_E;
+  int v[SCAN_E];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) {
+    v[k] = base + k < n ? in[base + k] : 0;
+    s += v[k];
+  }
+  int total;
+  int off = block_exclusive_scan(s, &total, sm);
+#pragma unroll
+  for (int k = 0; k < SCAN_E; k++) {
+    if (base + k < n) out[base + k] = off;
+    off += v[k];
+  }
+  if (threadIdx.x == 0) out[n] = total;
+}
+
 // out[0..n]: out[i] = sum(in[0..i-1]); out[n] = total.  in/out may not alias.
 int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t st) {
   if (n <= 0) {
     B2N_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(int32_t), st));
+    return 0;
+  }
+  if (n <= SCAN_SMALL) {
+    k_scan_small<<<1, 1024, 0, st>>>(in, out, (int)n);  B2N_LAUNCHED(1);
+    B2N_LAUNCH_OK();
     return 0;
   }
   const int nb = cdiv(n, SCAN_CH);
@@ -231,9 +259,10 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
                                                    const T *__restrict__ y, const T *__restrict__ z,
                                                    int32_t *__restrict__ hist, int32_t *__restrict__ dupes) {
   __shared__ int tkey[HT_N], tcnt[HT_N];
-  __shared__ int used;  // lanes merged in this CTA (> 0 <=> the table may hold entries)
+  __shared__ int used;    // lanes merged in this CTA
+  __shared__ int filled;  // the table holds entries
   for (int i = threadIdx.x; i < HT_N; i += blockDim.x) { tkey[i] = HT_EMPTY; tcnt[i] = 0; }
-  if (threadIdx.x == 0) used = 0;
+  if (threadIdx.x == 0) used = filled = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -261,6 +290,7 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
           const int old = atomicCAS(&tkey[h], HT_EMPTY, key);
           if (old == HT_EMPTY || old == key) {
             atomicAdd(&tcnt[h], n);
+            if (old == HT_EMPTY) filled = 1;
             done = true;
           }
         }
@@ -271,7 +301,7 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
   if (merged) atomicAdd(&used, merged);  // CTA total first: `dupes` is ONE address for the whole grid
   __syncthreads();
   if (threadIdx.x == 0 && used > 0) atomicAdd(dupes, used);
-  if (used)
+  if (filled)
     for (int i = threadIdx.x; i < HT_N; i += blockDim.x)
       if (tkey[i] != HT_EMPTY) atomicAdd(&hist[tkey[i]], tcnt[i]);
 }
@@ -583,8 +613,13 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     g.magic[d] = g.bin[d] > 1 ? (unsigned)(((1ull << 32) + g.bin[d] - 1) / g.bin[d]) : 0u;
   g.nsub = ps.nsub = (p.method == 3 && p.dim == 3) ? p.bin[2] : 1;
   g.swr_ns = p.method == 3 ? p.ns : 0;
-  const int nblk = (int)std::min<int64_t>(std::max<int64_t>(cdiv(M, 256), 1), 148 * 16);
+  // >= 1024 points per CTA: every CTA of the histogram pass sets up (and scans) its hot-key table
+  const int nblk = (int)std::min<int64_t>(std::max<int64_t>(cdiv(M, 1024), 1), 148 * 16);
   ps.sorted = p.opts.gpu_sort != 0 || p.method != 1;
+  // GM kernels on a fine grid that stays in L2 (<= 48 MB): the sort only buys locality the cache
+  // already provides, and at these sizes its launches cost more than they save (C1: 1-D, M = N =
+  // 1e6, c128: 0.305 ms sorted, 0.260 ms unsorted, reference cuFINUFFT 0.277 ms)
+  if (p.method == 1 && (size_t)p.nftot * sizeof(cpx<T>) <= (size_t(48) << 20)) ps.sorted = false;
   if (!ps.sorted) {
     if (M > 0) k_fold_only<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.rec);  B2N_LAUNCHED(1);
     B2N_LAUNCH_OK();
@@ -599,7 +634,7 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     dev_free(ps.key_start, st);
     ps.key_cnt = ps.key_start = nullptr;
     ps.cap_keys = 0;
-    if (int e = dev_alloc_t(&ps.key_cnt, (size_t)K, st)) return e;
+    if (int e = dev_alloc_t(&ps.key_cnt, (size_t)K + 8, st)) return e;  // [K]: merged-lane counter of P0
     if (int e = dev_alloc_t(&ps.key_start, (size_t)K + 1, st)) return e;
     ps.cap_keys = K;
   }
@@ -613,15 +648,14 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     ps.cap_bins = nbins;
   }
   if (!ps.bucket_cur)
-    if (int e = dev_alloc_t(&ps.bucket_cur, 256 + 8, st)) return e;
+    if (int e = dev_alloc_t(&ps.bucket_cur, 256, st)) return e;
   const int64_t sp_cap = std::min<int64_t>(nbins, M) + M / p.maxsub + 1;
   if (int e = grow(&ps.sp_bin, &ps.cap_sp, sp_cap, st)) return e;
   ps.sp_cap = sp_cap;
 
   // P0 + scan
-  B2N_CUDA_OK(cudaMemsetAsync(ps.key_cnt, 0, sizeof(int32_t) * K, st));
-  int32_t *dupes = ps.bucket_cur + 256;  // lanes merged by the histogram pass (clustering signal)
-  B2N_CUDA_OK(cudaMemsetAsync(dupes, 0, sizeof(int32_t), st));
+  int32_t *dupes = ps.key_cnt + K;  // lanes merged by the histogram pass (clustering signal)
+  B2N_CUDA_OK(cudaMemsetAsync(ps.key_cnt, 0, sizeof(int32_t) * (K + 1), st));
   const int64_t dupe_limit = M / 8;
   if (M > 0) k_key_hist<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.key_cnt, dupes);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
@@ -634,8 +668,10 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   {
     const int nb_blk = cdiv(nbins + 1, 256);
     k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, g.nsub, ps.key_start, p.maxsub, ps.bin_start, ps.key_cnt);  B2N_LAUNCHED(1);
-    if (int e = exclusive_scan_i32(ps.key_cnt, ps.sp_off, nbins, st)) return e;
-    k_sp_fill<<<cdiv(sp_cap, 256), 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);  B2N_LAUNCHED(1);
+    if (p.method != 1) {  // the GM kernels walk the sorted records directly
+      if (int e = exclusive_scan_i32(ps.key_cnt, ps.sp_off, nbins, st)) return e;
+      k_sp_fill<<<cdiv(sp_cap, 256), 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);  B2N_LAUNCHED(1);
+    }
     B2N_LAUNCH_OK();
   }
 
