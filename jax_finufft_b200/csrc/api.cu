@@ -103,12 +103,14 @@ template <typename T> Plan<T>::~Plan() {
   dev_free(prephase, st);
   dev_free(deconv, st);
   if (has_fft) cufftDestroy(fft);
+  if (pruned) { cufftDestroy(fft_z); for (int k = 0; k < 2; k++) if (slab_n[k]) cufftDestroy(fft_xy[k]); }
   delete inner;
 }
 
 template <typename T> void Plan<T>::set_stream(cudaStream_t s) {
   stream = s;
   if (has_fft) cufftSetStream(fft, s);
+  if (pruned) { cufftSetStream(fft_z, s); for (int k = 0; k < 2; k++) if (slab_n[k]) cufftSetStream(fft_xy[k], s); }
   if (inner) inner->set_stream(s);
 }
 
@@ -219,6 +221,38 @@ template <typename T> int Plan<T>::alloc_grid() {
     if (int e = dev_alloc_t(&fwker[d], (size_t)(nf[d] / 2 + 1), stream)) return e;
   }
   if (has_fft) { cufftDestroy(fft); has_fft = false; }
+  if (pruned) {
+    cufftDestroy(fft_z);
+    for (int k = 0; k < 2; k++) if (slab_n[k]) cufftDestroy(fft_xy[k]);
+    pruned = false;
+  }
+  const cufftType ft = sizeof(T) == 4 ? CUFFT_C2C : CUFFT_Z2Z;
+  static const char *no_prune = getenv("B2N_NO_PRUNED_FFT");
+  if (dim == 3 && type != 3 && !no_prune && 4 * ms[2] <= 3 * nf[2]) {
+    // planes that carry modes (deconvolve_wrapper.cu:91-111): [0, (N3-1)/2] and [nf3 - N3/2, nf3)
+    slab_lo[0] = 0;               slab_n[0] = (ms[2] - 1) / 2 + 1;
+    slab_lo[1] = nf[2] - ms[2] / 2; slab_n[1] = ms[2] / 2;
+    const long long plane = nf[0] * nf[1];
+    long long nz[1] = {(long long)nf[2]}, nxy[2] = {(long long)nf[1], (long long)nf[0]};
+    size_t work = 0;
+    bool ok = cufftCreate(&fft_z) == CUFFT_SUCCESS &&
+              cufftMakePlanMany64(fft_z, 1, nz, nz, plane, 1, nz, plane, 1, ft, plane, &work) == CUFFT_SUCCESS;
+    for (int k = 0; k < 2 && ok; k++) {
+      if (!slab_n[k]) continue;
+      ok = cufftCreate(&fft_xy[k]) == CUFFT_SUCCESS &&
+           cufftMakePlanMany64(fft_xy[k], 2, nxy, nxy, 1, plane, nxy, 1, plane, ft, slab_n[k], &work) == CUFFT_SUCCESS;
+    }
+    if (ok) {
+      pruned = true;
+      cufftSetStream(fft_z, stream);
+      for (int k = 0; k < 2; k++) if (slab_n[k]) cufftSetStream(fft_xy[k], stream);
+      return compute_fseries<T>(*this);
+    }
+    fprintf(stderr, "[b200nufft] pruned cufft plans failed; using the plain 3-D plan\n");
+    if (fft_z) cufftDestroy(fft_z);
+    for (int k = 0; k < 2; k++) { if (fft_xy[k]) cufftDestroy(fft_xy[k]); fft_xy[k] = 0; }
+    fft_z = 0;
+  }
   long long n[3];
   for (int d = 0; d < dim; d++) n[d] = nf[dim - 1 - d];  // slowest first
   if (cufftCreate(&fft) != CUFFT_SUCCESS) return B2N_ERR_CUDA_FAILURE;
@@ -396,7 +430,7 @@ template <typename T> int Plan<T>::exec_phase(int phase, void *cv, void *fkv) {
     if (phase & PH_END) {
       {
         StageTimer tm(dbg, stream, &timings[2]);
-        if (int e = run_fft(*this)) return e;
+        if (int e = run_fft(*this, ntransf)) return e;
       }
       StageTimer tm(dbg, stream, &timings[3]);
       if (int e = deconvolve<T>(*this, fw, fk, ntransf)) return e;
@@ -409,7 +443,7 @@ template <typename T> int Plan<T>::exec_phase(int phase, void *cv, void *fkv) {
       if (int e = amplify<T>(*this, fw, fk, ntransf)) return e;
     }
     StageTimer tm(dbg, stream, &timings[2]);
-    if (int e = run_fft(*this)) return e;
+    if (int e = run_fft(*this, ntransf)) return e;
   }
   if (phase & PH_BODY) {
     StageTimer tm(dbg, stream, &timings[4]);
@@ -447,8 +481,30 @@ int Plan<T>::interp(cpx<T> *c, const cpx<T> *postscale, const cpx<T> *grid, int 
   return method == 2 ? interp_tile<T>(*this, c, postscale, grid, ntr) : interp_gm<T>(*this, c, postscale, grid, ntr);
 }
 
-template <typename T> static int run_fft(Plan<T> &p) {
+template <typename T> static cufftResult fft_exec(cufftHandle h, cpx<T> *d, int dir) {
+  if (sizeof(T) == 4) return cufftExecC2C(h, (cufftComplex *)d, (cufftComplex *)d, dir);
+  return cufftExecZ2Z(h, (cufftDoubleComplex *)d, (cufftDoubleComplex *)d, dir);
+}
+
+// blk = transforms of the current batch that hold data
+template <typename T> static int run_fft(Plan<T> &p, int blk = -1) {
   const int dir = p.iflag >= 0 ? CUFFT_INVERSE : CUFFT_FORWARD;  // cufft_ex(.., iflag): types.h:108-115
+  if (p.pruned) {
+    // type 1: the grid is full, only the mode planes of the result are read  -> z first, then
+    //         (y, x) on the kept planes;  type 2: only the mode planes are non-zero -> (y, x) on
+    //         them first, then z everywhere.  (A DFT is separable: any order gives the same sum.)
+    const int nb = blk < 0 ? p.batch : blk;
+    const int64_t plane = p.nf[0] * p.nf[1];
+    for (int t = 0; t < nb; t++) {
+      cpx<T> *g = p.fw + (int64_t)t * p.nftot;
+      if (p.type == 1 && fft_exec<T>(p.fft_z, g, dir) != CUFFT_SUCCESS) return B2N_ERR_CUDA_FAILURE;
+      for (int k = 0; k < 2; k++)
+        if (p.slab_n[k] && fft_exec<T>(p.fft_xy[k], g + p.slab_lo[k] * plane, dir) != CUFFT_SUCCESS)
+          return B2N_ERR_CUDA_FAILURE;
+      if (p.type != 1 && fft_exec<T>(p.fft_z, g, dir) != CUFFT_SUCCESS) return B2N_ERR_CUDA_FAILURE;
+    }
+    return 0;
+  }
   cufftResult r;
   if (sizeof(T) == 4) r = cufftExecC2C(p.fft, (cufftComplex *)p.fw, (cufftComplex *)p.fw, dir);
   else r = cufftExecZ2Z(p.fft, (cufftDoubleComplex *)p.fw, (cufftDoubleComplex *)p.fw, dir);
@@ -475,7 +531,7 @@ template <typename T> int Plan<T>::exec1(cpx<T> *c, cpx<T> *fk) {
     if (opts.gpu_spreadinterponly) continue;
     {
       StageTimer tm(dbg, stream, &timings[2]);
-      if (int e = run_fft(*this)) return e;
+      if (int e = run_fft(*this, blk)) return e;
     }
     {
       StageTimer tm(dbg, stream, &timings[3]);
@@ -501,7 +557,7 @@ template <typename T> int Plan<T>::exec2(cpx<T> *c, cpx<T> *fk, const cpx<T> *po
       }
       {
         StageTimer tm(dbg, stream, &timings[2]);
-        if (int e = run_fft(*this)) return e;
+        if (int e = run_fft(*this, blk)) return e;
       }
       grid = fw;
     }

@@ -88,6 +88,12 @@ template <typename T> struct Plan : PlanBase {
   cpx<T> *fw = nullptr;                       // fine grid(s): batch * nftot
   cufftHandle fft = 0;
   bool has_fft = false;
+  // 3-D types 1/2: only N3 of the nf3 z-planes carry modes, so the (y, x) transforms of the other
+  // planes are never needed: one strided 1-D plan along z over the whole grid + batched 2-D plans
+  // on the two slabs of kept planes (2 passes over the data instead of 3)
+  cufftHandle fft_z = 0, fft_xy[2] = {0, 0};
+  int64_t slab_lo[2] = {0, 0}, slab_n[2] = {0, 0};
+  bool pruned = false;
 
   PointSet<T> pts;
 
