@@ -1,0 +1,86 @@
+"""Seeded sweep of the register kernels (3-D sliding window, 2-D register tile, stacked 2-D) over
+kernel widths, grid shapes, transform counts and mode orderings, against the CPU oracle
+(float64 restatement of the reference algorithm, oracle/nufft_oracle.c).  Point sets are dense
+enough that the register kernels are selected (checked through b2n_plan_info).  Tolerance:
+relative l2 <= 2 eps + the fp32 rounding floor of the case (tests/golden/cases.py::tolerance idea:
+a few 1e-7 per sqrt(#terms))."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+
+
+def _run(typ, nm, M, eps, ntr, iflag, modeord, seed, seam=False):
+    from jax_finufft_b200.plan import Plan
+
+    dim = len(nm)
+    rng = np.random.default_rng(seed)
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(dim)]
+    if seam:  # a third of the points pile up on the periodic seam, a few far outside [-pi, pi)
+        k = M // 3
+        for d in range(dim):
+            pts[d][:k] = (np.pi + rng.uniform(-0.2, 0.2, k)).astype(np.float32)
+            pts[d][k:k + 50] += np.float32(2 * np.pi * 3)
+    if typ == 1:
+        data = (rng.uniform(-1, 1, (ntr, M)) + 1j * rng.uniform(-1, 1, (ntr, M))).astype(np.complex64)
+    else:
+        data = (rng.uniform(-1, 1, (ntr,) + nm[::-1]) + 1j * rng.uniform(-1, 1, (ntr,) + nm[::-1])).astype(np.complex64)
+    p = Plan(typ, nm, n_trans=ntr, eps=eps, isign=iflag, modeord=modeord, upsampfac=2.0)
+    p.setpts(*[T(x) for x in pts])
+    out = p.execute(T(data)).cpu().numpy()
+    info = p.info()
+    p.destroy()
+    p64 = [x.astype(np.float64) for x in pts]
+    if typ == 1:
+        want = oracle.nufft1(nm, data, *p64, iflag=iflag, eps=eps, modeord=modeord, prec=1)
+    else:
+        want = oracle.nufft2(data, *p64, iflag=iflag, eps=eps, modeord=modeord, prec=1)
+    return out, want, info
+
+
+# (dim, nm (backend order, x first), M): grids with odd sizes, sizes that are not multiples of
+# the bins, and the smallest grid the register kernels take (nf = 32)
+GRIDS = [
+    ((16, 16), 3000), ((37, 50), 20000), ((64, 23), 20000), ((128, 96), 150000),
+    ((16, 16, 16), 20000), ((20, 33, 17), 40000), ((48, 18, 40), 120000),
+]
+EPS = [1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7]   # ns = 3 .. 8
+
+
+@pytest.mark.parametrize("typ", [1, 2])
+@pytest.mark.parametrize("eps", EPS)
+@pytest.mark.parametrize("nm,M", GRIDS, ids=[f"{'x'.join(map(str, g))}" for g, _ in GRIDS])
+def test_register_kernels_vs_oracle(nm, M, eps, typ):
+    seed = hash((nm, eps, typ)) % (2 ** 31)
+    out, want, info = _run(typ, nm, M, eps, 1, 1 if typ == 1 else -1, 0, seed, seam=True)
+    assert info.method == 3, "expected the register kernels for a dense float point set"
+    tol = 2 * eps + 3e-6
+    assert oracle.relerr(out, want) < tol, (nm, eps, typ, oracle.relerr(out, want))
+
+
+@pytest.mark.parametrize("ntr", [2, 3, 4, 5, 9])
+@pytest.mark.parametrize("typ", [1, 2])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_stacked_transforms_register_kernels(dim, typ, ntr):
+    """vmap-stacked transforms sharing the points: the 2-D stacked spreader handles 4 per pass
+    (remainders 1..3 exercised), the others run one transform per grid row."""
+    nm = (40, 28) if dim == 2 else (24, 18, 20)
+    out, want, info = _run(typ, nm, 30000, 1e-5, ntr, -1 if typ == 1 else 1, 1, 100 + ntr + 10 * dim, seam=False)
+    assert info.method == 3
+    assert out.shape == want.shape
+    for t in range(ntr):
+        assert oracle.relerr(out[t], want[t]) < 2e-5 + 3e-6, (dim, typ, ntr, t)
