@@ -71,35 +71,41 @@ __device__ __forceinline__ int fine_to_mode(int w, int ms, int nf, int modeord, 
   return p >= 0 ? p : ms + p;
 }
 
+// A CTA owns a tile of `cols` modes x 256/cols output rows (cols = a power of two <= 256 covering
+// ms[0], so short rows still fill the CTA); the row decode uses 32-bit arithmetic (the first
+// version decoded every mode with 64-bit divisions).
 template <typename T>
 __global__ void __launch_bounds__(256) k_deconvolve(const ModeGeom g, const cpx<T> *__restrict__ fw,
                                                      cpx<T> *__restrict__ fk,
                                                      const T *__restrict__ h1,
                                                      const T *__restrict__ h2,
                                                      const T *__restrict__ h3, int64_t nmodes,
-                                                     int64_t nftot) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nmodes) return;
+                                                     int64_t nftot, int nxchunk, int lgcols, unsigned rows) {
+  const int cols = 1 << lgcols, rpb = 256 >> lgcols;
+  const unsigned rb = blockIdx.x / (unsigned)nxchunk;
+  const int xc = (int)(blockIdx.x - rb * (unsigned)nxchunk);
+  const unsigned row = rb * rpb + (threadIdx.x >> lgcols);
+  const int k1 = xc * cols + (threadIdx.x & (cols - 1));
+  if (k1 >= g.ms[0] || row >= rows) return;
   fw += (int64_t)blockIdx.y * nftot;
-  fk += (int64_t)blockIdx.y * nmodes;
-  const int k1 = (int)(i % g.ms[0]);
-  const int64_t r = i / g.ms[0];
-  int w1, a1, w2 = 0, a2, w3 = 0, a3;
+  fk += (int64_t)blockIdx.y * nmodes + (int64_t)row * g.ms[0];
+  int w1, a1, w2 = 0, a2 = 0, w3 = 0, a3 = 0;
   mode_to_fine(k1, g.ms[0], g.nf[0], g.modeord, w1, a1);
-  T kv = h1[a1];
+  T kv = h1[a1];  // same association as before: ((h1 * h2) * h3)
   if (g.dim > 1) {
-    mode_to_fine((int)(r % g.ms[1]), g.ms[1], g.nf[1], g.modeord, w2, a2);
+    const unsigned k3 = row / (unsigned)g.ms[1], k2 = row - k3 * (unsigned)g.ms[1];
+    mode_to_fine((int)k2, g.ms[1], g.nf[1], g.modeord, w2, a2);
     kv *= h2[a2];
-  }
-  if (g.dim > 2) {
-    mode_to_fine((int)(r / g.ms[1]), g.ms[2], g.nf[2], g.modeord, w3, a3);
-    kv *= h3[a3];
+    if (g.dim > 2) {
+      mode_to_fine((int)k3, g.ms[2], g.nf[2], g.modeord, w3, a3);
+      kv *= h3[a3];
+    }
   }
   const cpx<T> v = fw[((int64_t)w3 * g.nf[1] + w2) * g.nf[0] + w1];
   cpx<T> o;
   o.x = v.x / kv;
   o.y = v.y / kv;
-  fk[i] = o;
+  fk[k1] = o;
 }
 
 template <typename T> int deconvolve(Plan<T> &p, const cpx<T> *fw, cpx<T> *fk, int ntr) {
@@ -107,9 +113,16 @@ template <typename T> int deconvolve(Plan<T> &p, const cpx<T> *fw, cpx<T> *fk, i
   g.dim = p.dim;
   g.modeord = p.opts.modeord;
   for (int d = 0; d < 3; d++) { g.ms[d] = (int)p.ms[d]; g.nf[d] = (int)p.nf[d]; }
-  dim3 grid((unsigned)cdiv(p.nmodes, 256), (unsigned)ntr);
+  int lgcols = 0;
+  while (lgcols < 8 && (1 << lgcols) < p.ms[0]) lgcols++;
+  const int cols = 1 << lgcols, rpb = 256 >> lgcols;
+  const int nxchunk = cdiv(p.ms[0], cols);
+  const int64_t rows = p.nmodes / p.ms[0];
+  const int64_t nblk = (int64_t)cdiv(rows, rpb) * nxchunk;
+  if (nblk > 0x7fffffffLL || rows > 0x7fffffffLL) return B2N_ERR_NDATA_NOTVALID;
+  dim3 grid((unsigned)nblk, (unsigned)ntr);
   k_deconvolve<T><<<grid, 256, 0, p.stream>>>(g, fw, fk, p.fwker[0], p.fwker[1], p.fwker[2],
-                                              p.nmodes, p.nftot);  B2N_LAUNCHED(1);
+                                              p.nmodes, p.nftot, nxchunk, lgcols, (unsigned)rows);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   return 0;
 }
