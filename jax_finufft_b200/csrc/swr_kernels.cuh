@@ -74,8 +74,11 @@ template <int NS> struct SwrCfg {
   static constexpr int ROW0 = KZO + KZW;
   // stride/4 odd: lane-strided 16-byte accesses of 8 consecutive lanes hit 8 distinct bank groups
   static constexpr int ROW = (ROW0 / 4) % 2 == 1 ? ROW0 : ROW0 + 4;
-  static constexpr int WARPS = 4;
-  static constexpr int MINB = NS <= 5 ? 5 : (NS <= 7 ? 4 : 2);  // CTAs per SM the register budget allows
+  // one warp per CTA: warps are independent, and a CTA's slot is then recycled the moment its
+  // subproblem ends instead of waiting for the slowest of four (measured at C3: interp 9.85 ->
+  // 9.0 ms, spread -0.7 %; two warps per CTA gave nothing)
+  static constexpr int WARPS = 1;
+  static constexpr int MINB = (NS <= 5 ? 5 : (NS <= 7 ? 4 : 2)) * 4;  // CTAs per SM the register budget allows
   static constexpr size_t smem_bytes() { return (size_t)WARPS * PB * ROW * sizeof(float); }
   static_assert(BX >= 1 && BY >= 1, "window too small");
   static_assert(CX == 1 || (BX % 2 == 0 && H % 2 == 0), "paired x cells must stay 16-byte aligned");
