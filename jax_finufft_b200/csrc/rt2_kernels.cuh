@@ -43,7 +43,7 @@ template <int NS> struct Rt2Cfg {
   static constexpr int KYO = 2 * WX;                   // ky[r = row & 3][s = row >> 2]
   static constexpr int ROW0 = KYO + WY;                // 48 floats
   static constexpr int ROW = ROW0 + 4;                 // stride / 4 odd
-  static constexpr int WARPS = 4;
+  static constexpr int WARPS = 1;  // one warp per CTA (see SwrCfg)
   static constexpr size_t spread_smem() { return (size_t)WARPS * PB * ROW * sizeof(float); }
   static constexpr size_t interp_warp_floats = PB * ROW + 2 * 16 * 33;
   static constexpr size_t interp_smem() { return (size_t)WARPS * interp_warp_floats * sizeof(float); }
