@@ -457,4 +457,115 @@ __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
   }
 }
 
+// ==================================================================================== INTERP, stacked
+// NT transforms sharing the points: NT register tiles per lane, the kernel vectors of a point are
+// loaded once, the partial results of every transform go through their own padded tile and are
+// reduced once per half batch.  Row layout as in the single-transform kernel ((kx, kx) pairs |
+// ky), written by rt2_weights with cv = (1, 1).
+template <int NS, int NT> struct Rt2NtiCfg {
+  using B = Rt2Cfg<NS>;
+  static constexpr size_t warp_floats = B::PB * B::ROW + (size_t)NT * 2 * 8 * 33;  // NT tiles of 8 points
+  static constexpr size_t smem() { return B::WARPS * warp_floats * sizeof(float); }
+};
+
+template <int NS, int NT>
+__global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
+    k_rt2_interp_nt(const SwrArgs a, const __grid_constant__ HornerTable<float> tab, int ntr) {
+  using C = Rt2Cfg<NS>;
+  using R = Rt2NtiCfg<NS, NT>;
+  constexpr int S = C::S, CX = C::CX;
+  extern __shared__ __align__(16) float swr_smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int first, cnt, x0, y0;
+  if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
+  float *rows = swr_smem + w * R::warp_floats;
+  float2 *RES = reinterpret_cast<float2 *>(rows + C::PB * C::ROW);   // [NT][8][33]
+  float2 *res_w = RES + lane;
+  const float2 *res_r = RES + (lane & 7) * 33 + (lane >> 3) * 8;  // this lane's 8 terms of a group sum
+  const int t0 = blockIdx.y * NT;
+  const int nt = min(NT, ntr - t0);
+  float2 *cout = a.cout + (int64_t)t0 * a.M;
+  const float2 *fw = a.fw + (int64_t)t0 * a.nftot;
+
+  const int r = lane >> 3, q = lane & 7;
+  const int xa = x0 - C::H, ya = y0 - C::H;
+  const int nf0 = a.nf[0], nf1 = a.nf[1];
+  float2 val[NT][S][CX];
+#pragma unroll
+  for (int t = 0; t < NT; t++)
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      const int gy = wrap_once(ya + 4 * s + r, nf1);
+#pragma unroll
+      for (int c = 0; c < CX; c++)
+        val[t][s][c] = t < nt ? __ldg(fw + (int64_t)t * a.nftot + (int64_t)gy * nf0 + wrap_once(xa + CX * q + c, nf0))
+                              : make_float2(0.f, 0.f);
+    }
+
+  Rt2Row pr;
+  const float *myx = rows + C::KXO + 2 * CX * q;
+  const float *myy = rows + C::KYO + S * r;
+  const PtRec<float> *recp = a.rec + first + lane;
+  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
+  for (int b0 = 0; b0 < cnt; b0 += C::PB) {
+    const int nb = min(C::PB, cnt - b0);
+    const float4 recB = b0 + C::PB + lane < cnt ? ld_stream4(recp + b0 + C::PB) : zrec;
+    const int orig = __float_as_int(recA.w);
+    float2 mine[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) mine[t] = make_float2(0.f, 0.f);
+    __syncwarp();
+    if (lane < nb) rt2_weights<NS>(tab, recA, make_float2(1.f, 1.f), xa, ya, rows + lane * C::ROW);
+    __syncwarp();
+    recA = recB;
+    pr.load_x(myx, 0);
+    pr.load_y(myy, 0);
+    int ro = 0, p = 0;
+    for (int grp = 0; grp * 8 < nb; grp++) {  // groups of 8 points: small result tiles (shared memory per warp)
+      const int tend = min(nb, 8 * grp + 8);
+      float2 *rw = res_w;
+      for (; p < tend; p++) {
+        const int ron = p + 1 < nb ? ro + C::ROW : ro;
+        const float2 k0 = pr.cxp(0), k1 = pr.cxp(1);
+        float2 k[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) k[s] = pr.kyp(s);
+        pr.load_x(myx, ron);
+        pr.load_y(myy, ron);
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+          float2 res = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int s = 0; s < S; s++) {
+            const float2 u = fma2(val[t][s][1], k1, mul2(val[t][s][0], k0));
+            res = fma2(u, k[s], res);
+          }
+          rw[t * (8 * 33)] = res;
+        }
+        rw += 33;
+        ro = ron;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        float2 s0 = res_r[t * (8 * 33)];
+#pragma unroll
+        for (int j = 1; j < 8; j++) s0 = add2(s0, res_r[t * (8 * 33) + j]);
+        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 8);
+        s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 8);
+        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);
+        s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);
+        if ((lane >> 3) == grp) mine[t] = s0;
+      }
+      __syncwarp();
+    }
+    if (lane < nb) {
+#pragma unroll
+      for (int t = 0; t < NT; t++)
+        if (t < nt) cout[(int64_t)t * a.M + orig] = mine[t];
+    }
+  }
+}
+
 }  // namespace b2n

@@ -93,6 +93,15 @@ template <int NS> struct Rt2Dispatch {
   static int interp(Plan<float> &p, const SwrArgs &a, int ntr) {
     if (p.ns == NS) {
       using C = Rt2Cfg<NS>;
+      if (ntr > 1 && !a.scale) {  // stacked transforms sharing the points
+        constexpr int NT = 4;
+        using R = Rt2NtiCfg<NS, NT>;
+        dim3 gridn((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)cdiv(ntr, NT));
+        B2N_CUDA_OK(cudaFuncSetAttribute(k_rt2_interp_nt<NS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R::smem()));
+        k_rt2_interp_nt<NS, NT><<<gridn, 32 * C::WARPS, R::smem(), p.stream>>>(a, p.tab, ntr);  B2N_LAUNCHED(1);
+        B2N_LAUNCH_OK();
+        return 0;
+      }
       dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
       B2N_CUDA_OK(cudaFuncSetAttribute(k_rt2_interp<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::interp_smem()));
       k_rt2_interp<NS><<<grid, 32 * C::WARPS, C::interp_smem(), p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
