@@ -27,16 +27,21 @@
 //   * per batch of 32 points, lane t evaluates the three kernel vectors of point t once (Horner,
 //     two intervals per FFMA2) and parks them in warp-private shared memory in the form the
 //     inner loop consumes: strength * x-weight as a complex pair per window column, y weights in
-//     (row mod 4, row / 4) order, z weights duplicated (w, w);
-//   * per point the warp then issues 6 LDS, 6 FMUL and 3 * ns FFMA2 (one instruction per complex
+//     (row mod 4, row / 4) order, z weights in plane order, stored ONCE each: FFMA2 / FMUL2 take
+//     a scalar-broadcast operand (R.F32), so no (w, w) pairs are needed -- and an LDS.128 costs
+//     four shared-memory wavefronts per warp whatever it broadcasts;
+//   * per point the warp then issues 4 LDS, 3 FMUL2 and 3 * ns FFMA2 (one instruction per complex
 //     cell update), straight-line: row slots a point's y window does not reach multiply by zero
-//     weights instead of branching (a branch per slot costs more issue slots than it saves and
-//     defeats the in-place register allocation of the accumulators).
+//     weights instead of branching or predicating (both measured slower).  Each
+//     piece of a point's weights is reloaded from the NEXT point's row right after its last use
+//     ("rolling" loads), so the loads have a whole FMA block to land;
+//   * one warp per CTA: warps are independent, and a CTA slot is recycled the moment its
+//     subproblem ends.
 // No shared or global atomics with return, no block barriers (warps are independent).
 //
 // Interpolation is the mirror image: the ring holds planes LOADED from the fine grid (64-byte
 // row segments, the next plane prefetched one step ahead); the cross-lane sum is done once per
-// group of 8 points through shared memory.
+// half batch (16 points) through a padded shared-memory tile, outside the phase chain.
 //
 // FFMA2/FMUL2 are emitted through the sm_100 intrinsics (__ffma2_rn): with inline-asm "+l"
 // operands ptxas routed half of the accumulators through temporaries (20 MOVs per point).
