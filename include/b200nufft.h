@@ -152,6 +152,14 @@ const char *b2n_strerror(int code);
 /* Drop every cached plan / workspace of the calling process (tests, memory pressure). */
 void b2n_cache_clear(void);
 
+/* Setpts cache (the reference re-sorts on every custom call,
+ * lib/kernels.cc.cu:49-51,64).  When on, setpts folds the coordinate arrays into a 64-bit
+ * signature and compares it on the device with that of the point set the (cached) plan already
+ * holds sorted; on a match the bin-sort kernels return at once -- no host round trip, the call
+ * stays stream-ordered.  Off by default (also: environment B2N_SETPTS_CACHE=1).  Returns the
+ * previous setting. */
+int b2n_set_setpts_cache(int on);
+
 /* Per-stage device timings (ms) of the most recent b2n_execute / b2n_setpts on this plan when
  * opts.debug != 0: [0] sort, [1] spread, [2] fft, [3] deconvolve/amplify, [4] interp,
  * [5] type-3 pre/post, [6] memset. */

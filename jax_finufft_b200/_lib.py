@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200nufft.so")
+# B2N_LIB: load another build of the same library (kernel A/B experiments; never a different backend)
+LIB_PATH = os.environ.get("B2N_LIB") or os.path.join(_HERE, "libb200nufft.so")
 _lib = None
 
 
@@ -63,7 +64,7 @@ EXPORTED = [
     "b2n_plan_info_get", "b2n_plan_sort_get", "b2n_plan_sort_copy", "b2n_run", "b2n_run_host", "b2n_cache_clear",
     "b2n_plan_timings", "b2n_setup_spreader", "b2n_next235beven", "b2n_set_nf_type12",
     "b2n_fseries", "b2n_horner_table", "b2n_default_binsize", "b2n_version", "b2n_launch_count",
-    "b2n_ffi_call", "b2n_ffi_arity", "b2n_ffi_targets", "b2n_strerror",
+    "b2n_ffi_call", "b2n_ffi_arity", "b2n_ffi_targets", "b2n_strerror", "b2n_set_setpts_cache",
 ]
 
 
@@ -108,6 +109,8 @@ def lib():
         L.b2n_strerror.argtypes = [ci]
         L.b2n_strerror.restype = C.c_char_p
         L.b2n_cache_clear.restype = None
+        L.b2n_set_setpts_cache.argtypes = [ci]
+        L.b2n_set_setpts_cache.restype = ci
         L.b2n_setup_spreader.argtypes = [dbl, dbl, ci, ci, C.POINTER(ci), C.POINTER(dbl)]
         L.b2n_next235beven.argtypes = [i64, i64]
         L.b2n_next235beven.restype = i64

@@ -1,6 +1,7 @@
 // api.cu -- plan lifecycle, the type 1/2/3 pipelines, the per-process plan cache and the C ABI.
 // Replaces lib/kernels.cc.cu (run_nufft), lib/cufinufft_wrapper.* and cuFINUFFT's
 // makeplan/setpts/execute/destroy (V/include/cufinufft/impl.h, V/src/cuda/{1,2,3}d/cufinufft*d.cu).
+#include <atomic>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -12,6 +13,18 @@
 namespace b2n {
 
 unsigned long long g_launch_count = 0;
+
+// setpts cache switch (sort.cu: binsort_points): -1 = not decided yet, read B2N_SETPTS_CACHE once
+static std::atomic<int> g_setpts_cache{-1};
+bool setpts_cache_enabled() {
+  int v = g_setpts_cache.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char *e = getenv("B2N_SETPTS_CACHE");
+    v = (e && e[0] && e[0] != '0') ? 1 : 0;
+    g_setpts_cache.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
 
 // ------------------------------------------------------------------------------------ utilities
 struct StageTimer {
@@ -100,6 +113,7 @@ template <typename T> Plan<T>::~Plan() {
   dev_free(pts.bin_start, st);
   dev_free(pts.sp_off, st);
   dev_free(pts.sp_bin, st);
+  dev_free(pts.sig, st);
   dev_free(prephase, st);
   dev_free(deconv, st);
   if (has_fft) cufftDestroy(fft);
@@ -690,6 +704,12 @@ extern "C" {
 const char *b2n_version(void) { return "b200nufft 0.1 (sm_100a)"; }
 
 unsigned long long b2n_launch_count(void) { return g_launch_count; }
+
+int b2n_set_setpts_cache(int on) {
+  const int prev = setpts_cache_enabled() ? 1 : 0;
+  g_setpts_cache.store(on ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
 
 void b2n_default_opts(b2n_opts *o) {  // defaults of V/src/cuda/cufinufft.cu:133-152
   std::memset(o, 0, sizeof(*o));

@@ -38,6 +38,10 @@ template <typename T> struct PointSet {
   int64_t sp_cap = 0;            // host-known upper bound on #subproblems
   int nsub = 1;                  // sub-keys per bin (z cells per bin for the SWR kernels)
   bool sorted = false;
+  // setpts cache (sort.cu): device {accumulator, signature of the sorted set, skip flag}
+  unsigned long long *sig = nullptr;
+  unsigned long long sig_salt = 0;  // M + sort geometry of the sorted set
+  bool sig_ok = false;              // the last binsort_points completed with the cache on
   int64_t cap_M = 0, cap_tmp = 0, cap_idx = 0, cap_keys = 0, cap_bins = 0, cap_sp = 0;
 };
 
@@ -172,6 +176,7 @@ void dev_free(void *p, cudaStream_t st);
 template <typename U> inline int dev_alloc_t(U **p, size_t count, cudaStream_t st) {
   return dev_alloc((void **)p, count * sizeof(U), st);
 }
-int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t st);
+int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t st, const int *skip = nullptr);
+bool setpts_cache_enabled();  // api.cu: b2n_set_setpts_cache / B2N_SETPTS_CACHE
 
 }  // namespace b2n

@@ -57,6 +57,10 @@ void dev_free(void *p, cudaStream_t st) {
   if (p) cudaFreeAsync(p, st);
 }
 
+// Setpts cache: every kernel of the sort takes a device flag and returns at once when it is set
+// (the flag is uniform over the grid and read before any barrier).  See binsort_points.
+#define B2N_SKIP_IF(p) do { if ((p) != nullptr && *(p) != 0) return; } while (0)
+
 // ------------------------------------------------------------------------------- scan (int32)
 constexpr int SCAN_T = 256;
 constexpr int SCAN_E = 8;  // elements per thread
@@ -92,7 +96,8 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total, int *sm /
 
 __global__ void __launch_bounds__(SCAN_T) k_scan_blocks(const int32_t *__restrict__ in,
                                                           int32_t *__restrict__ out, int64_t n,
-                                                          int32_t *__restrict__ bsum) {
+                                                          int32_t *__restrict__ bsum, const int *skip) {
+  B2N_SKIP_IF(skip);
   __shared__ int sm[33];
   const int64_t base = (int64_t)blockIdx.x * SCAN_CH + (int64_t)threadIdx.x * SCAN_E;
   int v[SCAN_E];
@@ -112,7 +117,8 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_blocks(const int32_t *__restric
   if (threadIdx.x == 0) bsum[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(1024) k_scan_bsum(int32_t *bsum, int nb, int32_t *grand) {
+__global__ void __launch_bounds__(1024) k_scan_bsum(int32_t *bsum, int nb, int32_t *grand, const int *skip) {
+  B2N_SKIP_IF(skip);
   __shared__ int sm[33];
   int carry = 0;
   for (int b0 = 0; b0 < nb; b0 += 1024) {
@@ -127,7 +133,8 @@ __global__ void __launch_bounds__(1024) k_scan_bsum(int32_t *bsum, int nb, int32
 }
 
 __global__ void __launch_bounds__(SCAN_T) k_scan_add(int32_t *__restrict__ out, int64_t n,
-                                                       const int32_t *__restrict__ bsum) {
+                                                       const int32_t *__restrict__ bsum, const int *skip) {
+  B2N_SKIP_IF(skip);
   const int64_t base = (int64_t)blockIdx.x * SCAN_CH + (int64_t)threadIdx.x * SCAN_E;
   const int add = bsum[blockIdx.x];
 #pragma unroll
@@ -138,7 +145,9 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_add(int32_t *__restrict__ out, 
 // small inputs (1-D plans, the per-bin subproblem counts of small grids): one block, one launch --
 // at M = 1e6 the sort is bound by launch gaps, not by bytes
 constexpr int SCAN_SMALL = 1024 * SCAN_E;
-__global__ void __launch_bounds__(1024) k_scan_small(const int32_t *__restrict__ in, int32_t *__restrict__ out, int n) {
+__global__ void __launch_bounds__(1024) k_scan_small(const int32_t *__restrict__ in, int32_t *__restrict__ out, int n,
+                                                     const int *skip) {
+  B2N_SKIP_IF(skip);
   __shared__ int sm[33];
   const int base = threadIdx.x * SCAN_E;
   int v[SCAN_E];
@@ -158,23 +167,24 @@ __global__ void __launch_bounds__(1024) k_scan_small(const int32_t *__restrict__
   if (threadIdx.x == 0) out[n] = total;
 }
 
-// out[0..n]: out[i] = sum(in[0..i-1]); out[n] = total.  in/out may not alias.
-int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t st) {
+// out[0..n]: out[i] = sum(in[0..i-1]); out[n] = total.  in/out may not alias.  `skip` (device flag,
+// may be null): non-zero turns every launch into a no-op (setpts cache, binsort_points).
+int exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t st, const int *skip) {
   if (n <= 0) {
     B2N_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(int32_t), st));
     return 0;
   }
   if (n <= SCAN_SMALL) {
-    k_scan_small<<<1, 1024, 0, st>>>(in, out, (int)n);  B2N_LAUNCHED(1);
+    k_scan_small<<<1, 1024, 0, st>>>(in, out, (int)n, skip);  B2N_LAUNCHED(1);
     B2N_LAUNCH_OK();
     return 0;
   }
   const int nb = cdiv(n, SCAN_CH);
   int32_t *bsum = nullptr;
   if (int e = dev_alloc_t(&bsum, (size_t)nb + 1, st)) return e;
-  k_scan_blocks<<<nb, SCAN_T, 0, st>>>(in, out, n, bsum);  B2N_LAUNCHED(1);
-  k_scan_bsum<<<1, 1024, 0, st>>>(bsum, nb, out + n);  B2N_LAUNCHED(1);
-  k_scan_add<<<nb, SCAN_T, 0, st>>>(out, n, bsum);  B2N_LAUNCHED(1);
+  k_scan_blocks<<<nb, SCAN_T, 0, st>>>(in, out, n, bsum, skip);  B2N_LAUNCHED(1);
+  k_scan_bsum<<<1, 1024, 0, st>>>(bsum, nb, out + n, skip);  B2N_LAUNCHED(1);
+  k_scan_add<<<nb, SCAN_T, 0, st>>>(out, n, bsum, skip);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   dev_free(bsum, st);
   return 0;
@@ -189,6 +199,7 @@ struct SortGeom {
   int nsub;    // 1, or bin[2]: sub-key = anchor z cell inside the bin (SWR kernels)
   int swr_ns;  // 0: reference bins (floor of the folded coordinate); else bins of ANCHOR cells
   unsigned magic[3];  // ceil(2^32 / bin[d]) (0 for bin 1): u / bin = umulhi(u, magic), u < 2^26
+  const int *skip;    // setpts cache: non-zero = these points are already sorted in the plan (or null)
 };
 
 // u / g.bin[d] without an integer division (the three runtime divides were a third of the
@@ -258,6 +269,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T *__restrict__ x,
                                                    const T *__restrict__ y, const T *__restrict__ z,
                                                    int32_t *__restrict__ hist, int32_t *__restrict__ dupes) {
+  B2N_SKIP_IF(g.skip);
   __shared__ int tkey[HT_N], tcnt[HT_N];
   __shared__ int used;    // lanes merged in this CTA
   __shared__ int filled;  // the table holds entries
@@ -328,6 +340,7 @@ __global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const
                                                      int64_t K, int shift, int nbuckets,
                                                      int32_t *__restrict__ bucket_cur,
                                                      PtRec<T> *__restrict__ tmp) {
+  B2N_SKIP_IF(g.skip);
   constexpr int E = PartCfg<T>::E, N = PT_T * E;
   __shared__ PtRec<T> srec[N];
   __shared__ unsigned short perm[N];
@@ -405,6 +418,7 @@ __global__ void __launch_bounds__(256) k_place(SortGeom g, int64_t M, const T *_
                                                 int32_t *__restrict__ key_cursor,
                                                 PtRec<T> *__restrict__ out,
                                                 const int32_t *__restrict__ dupes, int64_t dupe_limit) {
+  B2N_SKIP_IF(g.skip);
   if (dupes && *dupes > dupe_limit) return;  // clustered input: k_place_agg does the work
   const int lane = threadIdx.x & 31;
   const int64_t c0 = (int64_t)blockIdx.x * (256 * PL_E);
@@ -460,6 +474,7 @@ __global__ void __launch_bounds__(PA_T) k_place_agg(SortGeom g, int64_t M, const
                                                      int32_t *__restrict__ key_cursor,
                                                      PtRec<T> *__restrict__ out,
                                                      const int32_t *__restrict__ dupes, int64_t dupe_limit) {
+  B2N_SKIP_IF(g.skip);
   if (*dupes <= dupe_limit) return;
   extern __shared__ int pa_smem[];
   int *tkey = pa_smem, *tcnt = pa_smem + PA_HT;        // cnt doubles as the reserved base in phase 3
@@ -545,6 +560,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_fold_only(SortGeom g, int64_t M, const T *__restrict__ x,
                                                     const T *__restrict__ y, const T *__restrict__ z,
                                                     PtRec<T> *__restrict__ out) {
+  B2N_SKIP_IF(g.skip);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
     T xr, yr, zr;
@@ -563,7 +579,9 @@ __global__ void __launch_bounds__(256) k_extract_idx(int64_t M, const PtRec<T> *
 // bin_start[b] = key_start[b * nsub]; subproblems per bin = ceil(count / maxsub)
 // (precision_independent.cu:75-81)
 __global__ void k_sp_count(int64_t nbins, int nsub, const int32_t *__restrict__ key_start,
-                           int maxsub, int32_t *__restrict__ bin_start, int32_t *__restrict__ cnt) {
+                           int maxsub, int32_t *__restrict__ bin_start, int32_t *__restrict__ cnt,
+                           const int *skip) {
+  B2N_SKIP_IF(skip);
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b <= nbins) {
     const int s = key_start[b * nsub];
@@ -575,7 +593,8 @@ __global__ void k_sp_count(int64_t nbins, int nsub, const int32_t *__restrict__ 
 // its bin by bisection (a bin with thousands of subproblems -- clustered input -- used to be
 // filled by a single thread)
 __global__ void k_sp_fill(int64_t nbins, const int32_t *__restrict__ sp_off,
-                          int32_t *__restrict__ sp_bin, int64_t cap) {
+                          int32_t *__restrict__ sp_bin, int64_t cap, const int *skip) {
+  B2N_SKIP_IF(skip);
   const int64_t sp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (sp >= cap || sp >= sp_off[nbins]) return;
   int64_t lo = 0, hi = nbins;  // largest b with sp_off[b] <= sp
@@ -584,6 +603,56 @@ __global__ void k_sp_fill(int64_t nbins, const int32_t *__restrict__ sp_off,
     if (sp_off[mid] <= sp) lo = mid; else hi = mid;
   }
   sp_bin[sp] = (int32_t)lo;
+}
+
+
+// ------------------------------------------------------------------------------- setpts cache
+// jax-finufft re-sorts the points on every custom call
+// (lib/kernels.cc.cu:49-51,64), although forward, JVP and VJP of one step -- and every iteration
+// of a solver on a fixed trajectory -- present the same coordinates.  When enabled
+// (b2n_set_setpts_cache / B2N_SETPTS_CACHE=1) setpts first folds the coordinate arrays into a
+// 64-bit signature (one streaming read, 4*dim*M bytes) and compares it ON THE DEVICE with the
+// signature of the point set the plan holds sorted; on a match every sort kernel returns at
+// once.  No host round trip, so the call stays stream-ordered and graph-capturable.  The
+// signature is an order-dependent sum of avalanche-mixed (coordinate bits, index) words.
+__device__ __forceinline__ unsigned long long sig_mix(unsigned long long v) {  // splitmix64 finaliser
+  v ^= v >> 30; v *= 0xbf58476d1ce4e5b9ull;
+  v ^= v >> 27; v *= 0x94d049bb133111ebull;
+  return v ^ (v >> 31);
+}
+__device__ __forceinline__ unsigned long long sig_bits(float v) { return (unsigned long long)__float_as_uint(v); }
+__device__ __forceinline__ unsigned long long sig_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_pts_signature(int dim, int64_t M, const T *__restrict__ x,
+                                                        const T *__restrict__ y, const T *__restrict__ z,
+                                                        unsigned long long *__restrict__ acc) {
+  __shared__ unsigned long long part[8];
+  unsigned long long h = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+    unsigned long long v = sig_mix(sig_bits(x[i]) + 0x9e3779b97f4a7c15ull * (unsigned long long)(i + 1));
+    if (dim > 1) v = sig_mix(v ^ sig_bits(y[i]));
+    if (dim > 2) v = sig_mix(v ^ (sig_bits(z[i]) << 1));
+    h += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; w++) t += part[w];
+    atomicAdd(acc, t);
+  }
+}
+// sig[0]: accumulator of this setpts (left at zero), sig[1]: signature of the sorted point set,
+// sig[2]: the skip flag the sort kernels read
+__global__ void k_sig_decide(unsigned long long *sig, unsigned long long salt, int allow) {
+  const unsigned long long s = sig[0] ^ salt;
+  *reinterpret_cast<int *>(sig + 2) = (allow && s == sig[1]) ? 1 : 0;
+  sig[1] = s;
+  sig[0] = 0;
 }
 
 template <typename U> static int grow(U **p, int64_t *cap, int64_t need, cudaStream_t st) {
@@ -616,6 +685,28 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   // >= 1024 points per CTA: every CTA of the histogram pass sets up (and scans) its hot-key table
   const int nblk = (int)std::min<int64_t>(std::max<int64_t>(cdiv(M, 1024), 1), 148 * 16);
   ps.sorted = p.opts.gpu_sort != 0 || p.method != 1;
+  // setpts cache: same M and same sort geometry as the set this plan holds (=> no buffer below is
+  // reallocated) and, decided on the device, the same coordinate signature
+  g.skip = nullptr;
+  const bool was_ok = ps.sig_ok;
+  ps.sig_ok = false;
+  if (setpts_cache_enabled() && M > 0) {
+    if (!ps.sig) {
+      if (int e = dev_alloc_t(&ps.sig, 3, st)) return e;
+      B2N_CUDA_OK(cudaMemsetAsync(ps.sig, 0, 3 * sizeof(unsigned long long), st));
+    }
+    unsigned long long salt = 0x243f6a8885a308d3ull ^ (unsigned long long)M;
+    const int gw[] = {g.dim, g.nf[0], g.nf[1], g.nf[2], g.bin[0], g.bin[1], g.bin[2], g.nsub, g.swr_ns,
+                      p.method, p.maxsub, (int)ps.sorted, (int)sizeof(T)};
+    for (int w : gw) salt = (salt ^ (unsigned long long)(unsigned)w) * 0x100000001b3ull;
+    const int allow = was_ok && ps.sig_salt == salt;
+    ps.sig_salt = salt;
+    k_pts_signature<T><<<148 * 8, 256, 0, st>>>(g.dim, M, x, y, z, ps.sig);
+    k_sig_decide<<<1, 1, 0, st>>>(ps.sig, salt, allow);
+    B2N_LAUNCHED(2);
+    B2N_LAUNCH_OK();
+    g.skip = reinterpret_cast<const int *>(ps.sig + 2);
+  }
   // GM kernels on a fine grid that stays in L2 (<= 48 MB): the sort only buys locality the cache
   // already provides, and at these sizes its launches cost more than they save (C1: 1-D, M = N =
   // 1e6, c128: 0.305 ms sorted, 0.260 ms unsorted, reference cuFINUFFT 0.277 ms)
@@ -624,6 +715,7 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     if (M > 0) k_fold_only<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.rec);  B2N_LAUNCHED(1);
     B2N_LAUNCH_OK();
     ps.sp_cap = 0;
+    ps.sig_ok = g.skip != nullptr;
     return 0;
   }
   const int64_t nbins = p.nbins;
@@ -659,7 +751,7 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   const int64_t dupe_limit = M / 8;
   if (M > 0) k_key_hist<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.key_cnt, dupes);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
-  if (int e = exclusive_scan_i32(ps.key_cnt, ps.key_start, K, st)) return e;
+  if (int e = exclusive_scan_i32(ps.key_cnt, ps.key_start, K, st, g.skip)) return e;
 
   // subproblem list, entirely on device (the reference reads the total back and syncs,
   // V/src/cuda/3d/spread3d_wrapper.cu:479-487).  Derived from the scan BEFORE the placement pass
@@ -667,10 +759,10 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   // per-bin subproblem counts.
   {
     const int nb_blk = cdiv(nbins + 1, 256);
-    k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, g.nsub, ps.key_start, p.maxsub, ps.bin_start, ps.key_cnt);  B2N_LAUNCHED(1);
+    k_sp_count<<<nb_blk, 256, 0, st>>>(nbins, g.nsub, ps.key_start, p.maxsub, ps.bin_start, ps.key_cnt, g.skip);  B2N_LAUNCHED(1);
     if (p.method != 1) {  // the GM kernels walk the sorted records directly
-      if (int e = exclusive_scan_i32(ps.key_cnt, ps.sp_off, nbins, st)) return e;
-      k_sp_fill<<<cdiv(sp_cap, 256), 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap);  B2N_LAUNCHED(1);
+      if (int e = exclusive_scan_i32(ps.key_cnt, ps.sp_off, nbins, st, g.skip)) return e;
+      k_sp_fill<<<cdiv(sp_cap, 256), 256, 0, st>>>(nbins, ps.sp_off, ps.sp_bin, sp_cap, g.skip);  B2N_LAUNCHED(1);
     }
     B2N_LAUNCH_OK();
   }
@@ -701,6 +793,7 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     }
     B2N_LAUNCH_OK();
   }
+  ps.sig_ok = g.skip != nullptr;
   return 0;
 }
 

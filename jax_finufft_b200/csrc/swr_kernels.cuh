@@ -55,6 +55,9 @@
 
 namespace b2n {
 
+#ifndef SWR_S
+#define SWR_S 3
+#endif
 constexpr int SWR_BZ = 64;  // anchor z cells per bin (subproblems slide along them)
 constexpr int SWR_EMPTY = 0x40000000;
 
@@ -64,7 +67,7 @@ template <int NS> struct SwrCfg {
   static constexpr int CX = NS <= 7 ? 1 : 2; // x cells per lane
   static constexpr int WX = 8 * CX;          // window extent in x
   static constexpr int BX = CX == 1 ? WX - NS + 1 : ((WX - NS + 1) & ~1);  // bin extent (anchor cells)
-  static constexpr int S = 3;                // row slots per lane
+  static constexpr int S = SWR_S;            // row slots per lane
   static constexpr int WY = 4 * S;           // window extent in y
   static constexpr int BY = WY - NS + 1;
   static constexpr int BZ = SWR_BZ;
@@ -83,7 +86,11 @@ template <int NS> struct SwrCfg {
   // subproblem ends instead of waiting for the slowest of four (measured at C3: interp 9.85 ->
   // 9.0 ms, spread -0.7 %; two warps per CTA gave nothing)
   static constexpr int WARPS = 1;
-  static constexpr int MINB = (NS <= 5 ? 5 : (NS <= 7 ? 4 : 2)) * 4;  // CTAs per SM the register budget allows
+#ifdef SWR_MINB
+  static constexpr int MINB = SWR_MINB;
+#else
+  static constexpr int MINB = (NS <= 5 ? 5 : (NS <= 7 ? 4 : 2)) * 4;
+#endif  // CTAs per SM the register budget allows
   static constexpr size_t smem_bytes() { return (size_t)WARPS * PB * ROW * sizeof(float); }
   static_assert(BX >= 1 && BY >= 1, "window too small");
   static_assert(CX == 1 || (BX % 2 == 0 && H % 2 == 0), "paired x cells must stay 16-byte aligned");
