@@ -12,7 +12,7 @@
 
 namespace b2n {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 // setpts cache switch (sort.cu: binsort_points): -1 = not decided yet, read B2N_SETPTS_CACHE once
 static std::atomic<int> g_setpts_cache{-1};
@@ -652,28 +652,75 @@ struct CacheKey {
 struct CacheEntry {
   CacheKey key;
   PlanBase *plan;
-  cudaEvent_t done;
+  cudaEvent_t done;            // last use of the plan (null for graph-owned entries)
+  unsigned long long owner;    // 0, or the id of the stream capture this plan now belongs to
 };
 static std::mutex g_mu;
-static std::vector<CacheEntry> g_cache;
+static std::vector<CacheEntry> g_cache;   // free plans, oldest first
+static std::vector<CacheEntry> g_pinned;  // plans recorded into a CUDA graph (see cache_put)
 constexpr size_t CACHE_MAX = 8;
 
-static PlanBase *cache_take(const CacheKey &k, cudaStream_t st) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  for (size_t i = 0; i < g_cache.size(); i++)
-    if (g_cache[i].key == k) {
-      CacheEntry e = g_cache[i];
-      g_cache.erase(g_cache.begin() + i);
-      cudaStreamWaitEvent(st, e.done, 0);
-      cudaEventDestroy(e.done);
-      return e.plan;
-    }
-  return nullptr;
+// CUDA-graph capture.  A call made while its stream is capturing records the
+// plan's kernels, and with them the plan's buffers, into the graph: from then on the plan
+// belongs to that graph.  It is parked under the capture's id, handed out again only to calls of
+// the same capture (in-stream order protects it there) and never to eager callers; it lives
+// until b2n_cache_clear().  Eager calls after the capture build / take other plans.
+static unsigned long long capture_id(cudaStream_t st) {
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  if (cudaStreamGetCaptureInfo(st, &status, &id) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return status == cudaStreamCaptureStatusActive ? (id ? id : 1) : 0;
 }
-static void cache_put(const CacheKey &k, PlanBase *p, cudaStream_t st) {
+// Host-side CUDA calls that are "potentially unsafe" while some stream of the process captures in
+// global mode (event synchronisation, cudaMalloc inside cufftPlanMany): made in relaxed mode.
+struct RelaxedCapture {
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  bool on;
+  explicit RelaxedCapture(bool enable) : on(enable) { if (on) cudaThreadExchangeStreamCaptureMode(&mode); }
+  ~RelaxedCapture() { if (on) cudaThreadExchangeStreamCaptureMode(&mode); }
+};
+
+static PlanBase *cache_take(const CacheKey &k, cudaStream_t st, unsigned long long cid) {
+  CacheEntry e;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (cid)
+      for (size_t i = 0; i < g_pinned.size(); i++)
+        if (g_pinned[i].owner == cid && g_pinned[i].key == k) {
+          PlanBase *p = g_pinned[i].plan;
+          g_pinned.erase(g_pinned.begin() + i);
+          return p;  // same capture: ordered by the capture's own dependencies
+        }
+    size_t i = 0;
+    for (; i < g_cache.size(); i++)
+      if (g_cache[i].key == k) break;
+    if (i == g_cache.size()) return nullptr;
+    e = g_cache[i];
+    g_cache.erase(g_cache.begin() + i);
+  }
+  if (cid) {  // a dependency on an event outside the capture cannot be recorded: wait on the host
+    RelaxedCapture rc(true);
+    cudaEventSynchronize(e.done);
+  } else {
+    cudaStreamWaitEvent(st, e.done, 0);
+  }
+  cudaEventDestroy(e.done);
+  return e.plan;
+}
+static void cache_put(const CacheKey &k, PlanBase *p, cudaStream_t st, unsigned long long cid) {
   CacheEntry e;
   e.key = k;
   e.plan = p;
+  e.done = nullptr;
+  e.owner = cid;
+  if (cid) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_pinned.push_back(e);
+    return;
+  }
   cudaEventCreateWithFlags(&e.done, cudaEventDisableTiming);
   cudaEventRecord(e.done, st);
   PlanBase *evict = nullptr;
@@ -703,7 +750,7 @@ extern "C" {
 
 const char *b2n_version(void) { return "b200nufft 0.1 (sm_100a)"; }
 
-unsigned long long b2n_launch_count(void) { return g_launch_count; }
+unsigned long long b2n_launch_count(void) { return g_launch_count.load(std::memory_order_relaxed); }
 
 int b2n_set_setpts_cache(int on) {
   const int prev = setpts_cache_enabled() ? 1 : 0;
@@ -828,16 +875,19 @@ int b2n_plan_timings(b2n_plan plan, double *ms7) {
 }
 
 void b2n_cache_clear(void) {
-  std::vector<CacheEntry> old;
+  std::vector<CacheEntry> old, pinned;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     old.swap(g_cache);
+    pinned.swap(g_pinned);
   }
   for (auto &e : old) {
     cudaEventSynchronize(e.done);
     cudaEventDestroy(e.done);
     delete e.plan;
   }
+  if (!pinned.empty()) cudaDeviceSynchronize();  // graphs that recorded these plans must be gone by now
+  for (auto &e : pinned) delete e.plan;
 }
 
 // The body of b2n_run.  src_ready (optional): an event the stream must wait for before the first
@@ -876,13 +926,15 @@ static int run_core(int type, int dim, int is_double, cudaStream_t stream, doubl
   key.sort = o.gpu_sort; key.kerevalmeth = o.gpu_kerevalmeth; key.maxbatch = o.gpu_maxbatchsize;
   key.debug = o.debug;
 
-  PlanBase *p = cache_take(key, stream);
+  const unsigned long long cid = capture_id(stream);
+  PlanBase *p = cache_take(key, stream, cid);
   int warn = 0;
   if (p) {
     p->set_stream(stream);
   } else {
     b2n_plan h = nullptr;
     int64_t nk3[3] = {n_k ? n_k[0] : 1, n_k ? n_k[1] : 1, n_k ? n_k[2] : 1};
+    RelaxedCapture rc(cid != 0);  // cufftPlanMany allocates; the plan's own work is stream-ordered
     int ier = b2n_makeplan(type, dim, nk3, iflag, n_transf, eps, is_double, &h, &o);
     if (ier > 1) return ier;  // ret == 1 is a warning (kernels.cc.cu:52)
     warn = ier;
@@ -966,7 +1018,7 @@ static int run_core(int type, int dim, int is_double, cudaStream_t stream, doubl
     delete p;
     return B2N_ERR_CUDA_FAILURE;
   }
-  cache_put(key, p, stream);
+  cache_put(key, p, stream, cid);
   return warn;
 }
 

@@ -1,5 +1,6 @@
 // common.cuh -- shared device/host helpers for libb200nufft (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cufft.h>
 #include <stdint.h>
@@ -147,7 +148,7 @@ __device__ __forceinline__ void red_add(double2 *addr, double2 v) {
 }
 
 // number of kernels of THIS library launched by the calling process (bench.py's gpu_launches)
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;  // callers may be concurrent host threads
 #define B2N_LAUNCHED(n) (::b2n::g_launch_count += (n))
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
