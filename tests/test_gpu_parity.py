@@ -190,6 +190,38 @@ def test_binsort_contract_vs_oracle(method, dist):
         assert (d[same_bin] >= 0).all()
 
 
+@pytest.mark.parametrize("dist", ["uniform", "mixed"])
+def test_binsort_contract_partitioned_sort(dist):
+    """Point sets large enough for the partition pass P1 (records > 48 MB, sort.cu): same contract."""
+    from jax_finufft_b200.plan import Plan
+
+    rng = np.random.default_rng(12)
+    M, nm = 4_000_000, (64, 56, 60)
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(3)]
+    if dist == "mixed":  # a quarter of the points in a corner box: hot keys, below the aggregation threshold
+        n = M // 4
+        for d in range(3):
+            h = 2 * np.pi / (2 * nm[d])
+            pts[d][:n] = (-np.pi + rng.uniform(0, 8 * h, n)).astype(np.float32)
+        perm = rng.permutation(M)
+        pts = [x[perm] for x in pts]
+    p = Plan(1, nm, eps=1e-6).setpts(*[T(x) for x in pts])
+    info = p.info()
+    assert info.method == 3
+    idx, bstart = p.sort_arrays()
+    idx, bstart = idx.cpu().numpy(), bstart.cpu().numpy()
+    p.destroy()
+    nf = [int(info.nf[d]) for d in range(3)]
+    bins = [int(info.binsize[d]) for d in range(3)]
+    binid, hist, uz = oracle.binsort_anchor([x.astype(np.float64) for x in pts], nf, bins, int(info.ns), prec=1)
+    assert bstart[0] == 0 and bstart[-1] == M
+    assert (np.diff(bstart) == hist).all()
+    assert (np.sort(idx) == np.arange(M)).all()
+    assert (binid[idx] == np.repeat(np.arange(hist.size), hist)).all()
+    d = np.diff(uz[idx])
+    assert (d[np.diff(binid[idx]) == 0] >= 0).all()
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_clustered_at_the_periodic_seam(dim):
     """All points in a box 8 fine cells wide that STRADDLES x = +pi (the seam of the periodic grid):
