@@ -58,7 +58,10 @@ namespace b2n {
 #ifndef SWR_S
 #define SWR_S 3
 #endif
-constexpr int SWR_BZ = 64;  // anchor z cells per bin (subproblems slide along them)
+#ifndef SWR_BZ_N
+#define SWR_BZ_N 64
+#endif
+constexpr int SWR_BZ = SWR_BZ_N;  // anchor z cells per bin (subproblems slide along them)
 constexpr int SWR_EMPTY = 0x40000000;
 
 template <int NS> struct SwrCfg {

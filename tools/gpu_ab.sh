@@ -8,7 +8,7 @@ for L in "$@"; do
     python - <<PY
 import json
 d = json.load(open("$OUT/$W$L.json"))
-print("lib$L $W", round(d["ms_per_step"], 3), {k: round(v, 3) for k, v in d["stages_ms"].items() if v})
+print("lib$L $W", round(d["ms_per_step"], 3), {k: round(v, 3) for k, v in d.get("stages_ms", {}).items() if v})
 PY
   done
 done
