@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3_t1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true", help="skip also/e2e/cpu_baseline legs (profiling runs)")
-    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="points per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="points per CPU-baseline step")
     return ap.parse_args()
 
 
@@ -120,8 +120,9 @@ class ClockSampler:
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
 def cpu_port_rate(typ, M_full, nm, eps, sample, steps, warmup):
     """Times oracle/nufft_oracle.c (OpenMP, all host threads) on a bounded sample: the full
-    N=256^3 pipeline on `sample` points per step, plus one tiny-M run for the M-independent cost
-    (FFT + deconvolve), extrapolated linearly in M to the full workload."""
+    N=256^3 pipeline on `sample` points per step and, for the M-independent cost (FFT +
+    deconvolve), on sample/10 points -- both warm, same code path; the per-point cost is the slope
+    between the two, extrapolated linearly in M to the full workload."""
     import oracle
 
     rng = np.random.default_rng(1)
@@ -133,21 +134,26 @@ def cpu_port_rate(typ, M_full, nm, eps, sample, steps, warmup):
     else:
         d = rng.uniform(-1, 1, nm) + 1j * rng.uniform(-1, 1, nm)
         run = lambda n: oracle.nufft2(d, *x[:, :n], eps=eps, prec=1)
-    t0 = time.perf_counter(); run(1000); t_fixed = time.perf_counter() - t0
+
+    def clock(n):
+        t0 = time.perf_counter(); run(n); return time.perf_counter() - t0
+
+    small = max(1000, sample // 10)
+    clock(small)                                  # first touch of the grids, thread pool, FFT tables
+    t_small = min(clock(small), clock(small))
     for _ in range(max(0, warmup - 1)):
         run(sample)
-    ts = []
-    for _ in range(steps):
-        t0 = time.perf_counter(); run(sample); ts.append(time.perf_counter() - t0)
-    t_step = statistics.mean(ts)
-    per_pt = max(t_step - t_fixed, 1e-9) / sample
+    t_step = statistics.mean(clock(sample) for _ in range(steps))
+    per_pt = max(t_step - t_small, 0.0) / (sample - small)
+    t_fixed = max(t_small - per_pt * small, 0.0)
     t_full = t_fixed + per_pt * M_full
     return {
         "value": M_full / t_full, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
         "sample": (f"oracle/nufft_oracle.c (float64 restatement, OpenMP x{oracle.num_threads()}): {steps} steps of the full "
-                   f"N=256^3 pipeline on {sample} points ({t_step:.2f} s/step, of which {t_fixed:.2f} s is M-independent "
-                   f"FFT/deconvolve), extrapolated linearly in M to M={M_full}: {t_full:.1f} s; the reference CPU FINUFFT "
-                   "(xsimd+FFTW) cannot be built offline (SURVEY.md §8c)"),
+                   f"N=256^3 pipeline on {sample} points ({t_step:.2f} s/step; {t_small:.2f} s on {small} points => "
+                   f"{per_pt * 1e9:.0f} ns/point + {t_fixed:.2f} s M-independent FFT/deconvolve), extrapolated linearly "
+                   f"in M to M={M_full}: {t_full:.1f} s; the reference CPU FINUFFT (xsimd+FFTW) cannot be built offline "
+                   "(SURVEY.md §8c)"),
         "ms_per_step_extrapolated": t_full * 1e3,
     }
 
