@@ -380,7 +380,8 @@ def main_ours(a):
 
         # ---- N > 1: the one path with a real exchange step: ONE 3-D type 1 with its
         # M points split across the ranks by index range (strong scaling of a single transform).
-        # reduce_scatter = native path (private fine grids summed by NCCL reduce-scatter over
+        # slab = spatial split (points exchanged by z-slab, spread into slab + halo, halo planes to the
+        # neighbours); reduce_scatter = native path (private fine grids summed by NCCL reduce-scatter over
         # NVLink, slab/pencil FFT divided by N); psum = what jax-finufft gets from shard_map
         # (every rank runs the full FFT, all-reduce of the output modes).
         if world > 1 and a.workload == "c3_t1":
@@ -392,12 +393,25 @@ def main_ours(a):
             del w
             torch.cuda.empty_cache()
             sharded = {}
-            for mode in ("reduce_scatter", "psum"):
+            for mode in ("slab", "reduce_scatter", "psum"):
                 fn = lambda: P.nufft1_sharded_points(nm, lc, *lp, combine=mode, gather=False, eps=eps, iflag=1)
                 ms_s, _ = timed(fn, 3, 2)
                 sharded[mode] = {"value": world * Ml / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s,
                                  "M_total": world * Ml, "scaling": "strong"}
             line["also"]["c3_t1_points_sharded"] = sharded
+            # the same three paths where the uniform-grid work dominates: N = 512^3 (fine grid 1024^3 =
+            # 8.6 GB, FFT ~ 9 ms on one GPU).  psum repeats that FFT on every rank and reduce_scatter
+            # moves the whole private grid; the slab split divides both by the number of ranks.
+            nm5 = (512, 512, 512)
+            big = {}
+            for mode in ("slab", "reduce_scatter", "psum"):
+                torch.cuda.empty_cache()
+                fn = lambda: P.nufft1_sharded_points(nm5, lc, *lp, combine=mode, gather=False, eps=eps, iflag=1)
+                ms_s, _ = timed(fn, 2, 1)
+                big[mode] = {"value": world * Ml / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s,
+                             "M_total": world * Ml, "N": list(nm5), "scaling": "strong"}
+                L.b2n_cache_clear()
+            line["also"]["t1_n512_points_sharded"] = big
             del lp, lc
 
         # ---- CPU baseline: the oracle port on the host cores (rank 0, N=1 only)

@@ -64,7 +64,7 @@ EXPORTED = [
     "b2n_plan_info_get", "b2n_plan_sort_get", "b2n_plan_sort_copy", "b2n_run", "b2n_run_host", "b2n_cache_clear",
     "b2n_plan_timings", "b2n_setup_spreader", "b2n_next235beven", "b2n_set_nf_type12",
     "b2n_fseries", "b2n_horner_table", "b2n_default_binsize", "b2n_version", "b2n_launch_count",
-    "b2n_ffi_call", "b2n_ffi_arity", "b2n_ffi_targets", "b2n_strerror", "b2n_set_setpts_cache",
+    "b2n_ffi_call", "b2n_ffi_arity", "b2n_ffi_targets", "b2n_strerror", "b2n_set_setpts_cache", "b2n_slab_partition",
 ]
 
 
@@ -110,6 +110,7 @@ def lib():
         L.b2n_strerror.restype = C.c_char_p
         L.b2n_cache_clear.restype = None
         L.b2n_set_setpts_cache.argtypes = [ci]
+        L.b2n_slab_partition.argtypes = [ci, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, vp]
         L.b2n_set_setpts_cache.restype = ci
         L.b2n_setup_spreader.argtypes = [dbl, dbl, ci, ci, C.POINTER(ci), C.POINTER(dbl)]
         L.b2n_next235beven.argtypes = [i64, i64]

@@ -27,6 +27,13 @@ that its cost is divided by G instead of repeated G times:
     all_to_all transpose: z-slabs -> y-pencils                   [NCCL]
     1-D FFT along z, crop to N3, divide by the kernel Fourier series (deconvolve)
 
+``combine="slab"`` goes one step further (the *spatial* split): the points are first exchanged so
+that every GPU holds the points of its own nf3/G z-slabs (ONE all_to_all of 20 bytes per point),
+each GPU spreads into a grid of just its slabs plus a halo of ceil(ns/2)+2 planes on either side,
+and only the halo planes (2 x 6 planes, 25 MB at C3 instead of the 1.07 GB private grid) travel to
+the two neighbours.  Sort, spread and grid memory are all divided by G; the slab/pencil FFT is
+the same.
+
 The output is sharded over the y mode axis (``gather=True`` all-gathers it).  The psum path is
 kept as the parity check.  All collectives are enqueued on the current CUDA stream; there is no
 host synchronisation inside.  With the ``gloo`` backend (CPU tests) the post-spread stages run on
@@ -46,7 +53,7 @@ from .ops import get_frequency_array, nufft1, nufft2, nufft3
 __all__ = [
     "shard_range", "split_transforms", "nufft1_stacked", "nufft2_stacked", "nufft1_sharded_points",
     "nufft2_sharded_points", "nufft3_sharded_sources", "nufft3_sharded_targets", "fine_grid_geometry",
-    "slab_pencil_fft", "reduce_scatter_slabs",
+    "slab_pencil_fft", "reduce_scatter_slabs", "exchange_points_by_slab", "halo_add", "slab_halo",
 ]
 
 
@@ -228,18 +235,147 @@ def slab_pencil_fft(slab, output_shape, nf, iflag, ns, beta, modeord=0, group=No
     return out
 
 
+# ---------------------------------------------------------------------------- spatial (slab) split
+def slab_halo(ns):
+    """Halo planes on either side of a rank's z-slabs: the ns-wide window of a point inside the
+    slab reaches at most ceil(ns/2) planes out; +2 keeps float32 rounding of the re-based
+    coordinate away from the local grid's periodic seam."""
+    return (int(ns) + 1) // 2 + 2
+
+
+def _rows_all_to_all(rows, counts, group):
+    """rows (M, W) grouped by destination rank, counts[r] rows for rank r -> the rows every rank
+    sent to this one.  NCCL: all_to_all_single; gloo (CPU tests): all_gather + slice."""
+    world, rank = _world(group)
+    if world == 1:
+        return rows
+    cnt = counts.to(torch.int64) if torch.is_tensor(counts) else torch.as_tensor(counts, dtype=torch.int64, device=rows.device)
+    if rows.is_cuda:
+        got = torch.empty_like(cnt)
+        dist.all_to_all_single(got, cnt, group=group)
+        sent, got = torch.stack([cnt, got]).tolist()  # the one host read of this path: the split sizes
+        out = torch.empty((sum(got), rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        dist.all_to_all_single(out, rows, output_split_sizes=got, input_split_sizes=sent, group=group)
+        return out
+    allc = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(allc, cnt, group=group)
+    mmax = int(max(int(c.sum()) for c in allc))
+    pad = torch.zeros((mmax, rows.shape[1]), dtype=rows.dtype)
+    pad[: rows.shape[0]] = rows
+    allr = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(allr, pad, group=group)
+    parts = []
+    for src in range(world):
+        off = int(allc[src][:rank].sum())
+        parts.append(allr[src][off: off + int(allc[src][rank])])
+    return torch.cat(parts, 0)
+
+
+def exchange_points_by_slab(source_local, points_local, nf0, ns, group=None):
+    """Send every point to the rank that owns its fine-grid plane along axis 0 (the slowest grid
+    axis, points_local[0]); rank r owns planes [r*L, (r+1)*L), L = nf0 / G.
+
+    Returns (source, points, Lz): the strengths and points this rank received, with the axis-0
+    coordinate RE-BASED to the rank's local grid of Lz = L + 2*halo planes (plane p of the local grid
+    = global plane r*L - halo + p) and expressed as an angle in [-pi, pi) of that local grid, so
+    that the unmodified spreader (which folds its input periodically) places it correctly.  The
+    re-basing is done in float64 by the sender; the float32 the spreader sees is as accurate,
+    in cells, as the original coordinate was."""
+    world, rank = _world(group)
+    L = int(nf0) // world
+    h = slab_halo(ns)
+    Lz = L + 2 * h
+    z = points_local[0]
+    rdt = z.dtype
+    if z.is_cuda and len(points_local) == 3:  # one native pass (csrc/slab.cu) instead of ~20 torch kernels
+        M = z.numel()
+        cdt = torch.complex64 if rdt == torch.float32 else torch.complex128
+        pp = [q.to(rdt).contiguous() for q in points_local]
+        cc = source_local.to(cdt).contiguous()
+        rows = torch.empty((M, 5), dtype=rdt, device=z.device)
+        cnt = torch.empty(2 * world, dtype=torch.int64, device=z.device)
+        vp = C.c_void_p
+        ier = _lib.lib().b2n_slab_partition(int(rdt == torch.float64), vp(torch.cuda.current_stream(z.device).cuda_stream),
+                                            M, vp(pp[0].data_ptr()), vp(pp[1].data_ptr()), vp(pp[2].data_ptr()),
+                                            vp(cc.data_ptr()), int(nf0), world, h, vp(rows.data_ptr()), vp(cnt.data_ptr()))
+        if ier:
+            raise RuntimeError(f"b2n_slab_partition failed with code {ier}")
+        if world > 1:
+            rows = _rows_all_to_all(rows, cnt[:world], group)
+        pts = [rows[:, d].contiguous() for d in range(3)]
+        return torch.complex(rows[:, 3].contiguous(), rows[:, 4].contiguous()), pts, Lz
+    two_pi = 2.0 * np.pi
+    t = z.to(torch.float64) / two_pi + 0.5
+    zf = (t - torch.floor(t)) * float(nf0)                       # fold_rescale (csrc/common.cuh), in float64
+    owner = torch.clamp((zf / L).floor().to(torch.int64), 0, world - 1)
+    z_in = ((zf - (owner * L).to(torch.float64) + h) * (two_pi / Lz) - np.pi).to(rdt)
+    rows = torch.stack([z_in] + [q.to(rdt) for q in points_local[1:]] +
+                       [source_local.real.to(rdt), source_local.imag.to(rdt)], dim=1)
+    if world > 1:
+        order = torch.argsort(owner)
+        rows = rows.index_select(0, order)
+        counts = torch.bincount(owner, minlength=world).tolist()
+        rows = _rows_all_to_all(rows.contiguous(), counts, group)
+    nd = len(points_local)
+    pts = [rows[:, d].contiguous() for d in range(nd)]
+    src = torch.complex(rows[:, nd].contiguous(), rows[:, nd + 1].contiguous())
+    return src, pts, Lz
+
+
+def halo_add(local, h, group=None):
+    """local (L + 2h, ...) spread by this rank -> its L summed planes: the h planes below / above the
+    slab belong to the previous / next rank (periodically) and are added there."""
+    world, rank = _world(group)
+    Lz = local.shape[0]
+    L = Lz - 2 * h
+    if L < h:
+        raise ValueError(f"slab of {L} planes is thinner than the halo ({h})")
+    lo, hi = local[:h], local[L + h:]
+    if world == 1:
+        local[L: L + h] += lo
+        local[h: 2 * h] += hi
+        return local[h: L + h]
+    prev, nxt = (rank - 1) % world, (rank + 1) % world
+    lo_s, hi_s = lo.contiguous(), hi.contiguous()
+    from_next, from_prev = torch.empty_like(lo_s), torch.empty_like(hi_s)
+    # gloo has no complex send/recv: move the real views
+    v = torch.view_as_real
+    ops = [dist.P2POp(dist.isend, v(lo_s), prev, group=group, tag=1),
+           dist.P2POp(dist.isend, v(hi_s), nxt, group=group, tag=2),
+           dist.P2POp(dist.irecv, v(from_next), nxt, group=group, tag=1),
+           dist.P2POp(dist.irecv, v(from_prev), prev, group=group, tag=2)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    slab = local[h: L + h]
+    slab[L - h:] += from_next   # the next rank's low halo = my top planes
+    slab[:h] += from_prev       # the previous rank's high halo = my bottom planes
+    return slab
+
+
+_SPREAD_PLANS = {}  # spread-only plans, kept across calls (sort workspaces are grow-only)
+
+
 def _spread_only(nf, c, pts, eps, iflag, upsampfac):
     """Private fine grid (nf3, nf2, nf1) of this rank's points: the backend's spreader alone
     (gpu_spreadinterponly, V/include/cufinufft/impl.h:115-117) with the type-1 plan's kernel."""
     from .plan import Plan
 
-    p = Plan(1, tuple(nf[::-1]), n_trans=1, eps=eps, isign=iflag, dtype=str(c.dtype).replace("torch.", ""),
-             gpu_spreadinterponly=1, upsampfac=float(upsampfac))
+    key = (tuple(int(n) for n in nf), str(c.dtype), float(eps), int(iflag), float(upsampfac), c.device.index,
+           torch.cuda.current_stream(c.device).cuda_stream)  # a plan enqueues on the stream it was made on
+    p = _SPREAD_PLANS.pop(key, None)
+    if p is None:
+        p = Plan(1, tuple(nf[::-1]), n_trans=1, eps=eps, isign=iflag, dtype=str(c.dtype).replace("torch.", ""),
+                 gpu_spreadinterponly=1, upsampfac=float(upsampfac))
     try:
         p.setpts(*pts[::-1])  # backend order: x (fastest) first
-        return p.execute(c.reshape(1, -1))[0]
-    finally:
+        out = p.execute(c.reshape(1, -1))[0]
+    except Exception:
         p.destroy()
+        raise
+    while len(_SPREAD_PLANS) >= 4:
+        _SPREAD_PLANS.pop(next(iter(_SPREAD_PLANS))).destroy()
+    _SPREAD_PLANS[key] = p
+    return out
 
 
 def nufft1_sharded_points(output_shape, source_local, *points_local, group=None, combine="reduce_scatter",
@@ -251,15 +387,24 @@ def nufft1_sharded_points(output_shape, source_local, *points_local, group=None,
                               (sharding_test.py:163-165).  Output replicated.
     combine="reduce_scatter"  native path (module docstring).  3-D, single transform.  Output
                               y-sharded (N3, N2_local, N1) unless ``gather``.
+    combine="slab"            spatial split (module docstring): points exchanged by z-slab, spread
+                              into slab + halo, halo planes added at the neighbours.  Same output.
     """
     world, _ = _world(group)
+    if combine == "auto":
+        # measured on B200 (DESIGN.md section 6): the exchange of the slab split costs about what one
+        # 512^3 fine-grid FFT does, so it pays once the fine grid is larger than that
+        nftot = 1
+        for n in output_shape:
+            nftot *= 2 * int(n)
+        combine = "slab" if (len(points_local) == 3 and source_local.ndim == 1 and nftot > 300_000_000) else "psum"
     if combine == "psum" or len(points_local) != 3 or source_local.ndim != 1:
         out = nufft1(output_shape, source_local, *points_local, iflag=iflag, eps=eps, opts=opts)
         if world > 1:
             dist.all_reduce(torch.view_as_real(out), group=group)
         return out
-    if combine != "reduce_scatter":
-        raise ValueError("combine must be 'psum' or 'reduce_scatter'")
+    if combine not in ("reduce_scatter", "slab"):
+        raise ValueError("combine must be 'psum', 'reduce_scatter', 'slab' or 'auto'")
     from . import options
 
     o = options.unpack_opts(opts, 1, True) or options.Opts()
@@ -269,8 +414,13 @@ def nufft1_sharded_points(output_shape, source_local, *points_local, group=None,
     if nf[0] % world:
         return nufft1_sharded_points(output_shape, source_local, *points_local, group=group, combine="psum",
                                      iflag=iflag, eps=eps, opts=opts)
-    grid = _spread_only(nf, source_local, list(points_local), eps, iflag, o.gpu_upsampfac)
-    slab = reduce_scatter_slabs(grid, group)
-    del grid
+    if combine == "slab" and nf[0] // world >= 2 * slab_halo(ns):
+        src, pts, Lz = exchange_points_by_slab(source_local, list(points_local), nf[0], ns, group)
+        local = _spread_only((Lz, nf[1], nf[2]), src, pts, eps, iflag, o.gpu_upsampfac)
+        slab = halo_add(local, slab_halo(ns), group)
+    else:
+        grid = _spread_only(nf, source_local, list(points_local), eps, iflag, o.gpu_upsampfac)
+        slab = reduce_scatter_slabs(grid, group)
+        del grid
     return slab_pencil_fft(slab, output_shape, nf, iflag, ns, beta, modeord=int(o.modeord), group=group,
                            gather=gather)

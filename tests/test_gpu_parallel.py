@@ -31,6 +31,22 @@ def _data(M, nm, seed, dev):
 
 
 @pytest.mark.parametrize("nm,iflag", [((24, 20, 16), 1), ((16, 18, 30), -1)])
+def test_slab_split_single_gpu(nm, iflag):
+    """combine="slab" with world = 1: the whole grid is one slab whose halo wraps onto itself."""
+    import jax_finufft_b200 as J
+    import oracle
+    from jax_finufft_b200 import parallel as P
+
+    dev = torch.device("cuda:0")
+    tp, tc, pts, c = _data(30000, nm, 4, dev)
+    tp[0][:4] = torch.tensor([-np.pi, 0.0, np.nextafter(np.float32(np.pi), np.float32(0)), 3 * np.pi], device=dev)
+    a = P.nufft1_sharded_points(nm, tc, *tp, combine="slab", iflag=iflag, eps=1e-6)
+    b = J.nufft1(nm, tc, *tp, iflag=iflag, eps=1e-6)
+    assert a.shape == b.shape == tuple(nm)
+    assert oracle.relerr(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("nm,iflag", [((24, 20, 16), 1), ((16, 18, 30), -1)])
 def test_native_type1_pipeline_single_gpu(nm, iflag):
     """spread-only plan + slab/pencil FFT + deconvolve == the fused single-GPU nufft1 (<= 2 eps)
     and the oracle."""
@@ -66,6 +82,13 @@ def _worker(rank, world, port, ret):
         res = {}
         a = P.nufft1_sharded_points(nm, tc[lo:hi].contiguous(), *loc, combine="reduce_scatter", eps=1e-6)
         res["rs"] = oracle.relerr(a.cpu().numpy(), full.cpu().numpy())
+        for gather in (True, False):
+            a = P.nufft1_sharded_points(nm, tc[lo:hi].contiguous(), *loc, combine="slab", eps=1e-6, gather=gather)
+            if not gather:
+                ylo, yhi = P.shard_range(nm[1], world, rank)
+                res["slab_sharded"] = oracle.relerr(a.cpu().numpy(), full[:, ylo:yhi].cpu().numpy())
+            else:
+                res["slab"] = oracle.relerr(a.cpu().numpy(), full.cpu().numpy())
         b = P.nufft1_sharded_points(nm, tc[lo:hi].contiguous(), *loc, combine="psum", eps=1e-6)
         res["psum"] = oracle.relerr(b.cpu().numpy(), full.cpu().numpy())
         f = torch.as_tensor((np.random.default_rng(9).uniform(-1, 1, nm) + 0j).astype(np.complex64), device=dev)

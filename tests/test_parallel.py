@@ -76,6 +76,53 @@ def test_reduce_scatter_path_matches_single_process_oracle(nm, iflag, modeord, g
         assert ret[r] < 1e-12, dict(ret)   # same arithmetic as the oracle, only the FFT library differs
 
 
+def _worker_slab(rank, world, port, nm, M, iflag, ret):
+    """Spatial split: exchange by z-slab -> (oracle) spread into slab + halo -> halo add -> slab/pencil FFT."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle
+        from jax_finufft_b200 import parallel as P
+
+        eps = 1e-6
+        pts, c = _inputs(M, 8)
+        # points on the slab boundaries, at the periodic seam and just beside them
+        pts[0, :6] = [-np.pi, 0.0, np.nextafter(0.0, -1), np.nextafter(np.pi, 0), 1e-9, -np.pi + 1e-9]
+        lo, hi = P.shard_range(M, world, rank)
+        ns, beta, nf = P.fine_grid_geometry(nm, eps, single=False)
+        h = P.slab_halo(ns)
+        src, loc, Lz = P.exchange_points_by_slab(torch.from_numpy(c[lo:hi]), [torch.from_numpy(p[lo:hi]) for p in pts],
+                                                 nf[0], ns)
+        assert Lz == nf[0] // world + 2 * h
+        n_all = torch.tensor([src.numel()])
+        dist.all_reduce(n_all)
+        assert int(n_all) == M                                  # nobody lost or duplicated
+        L = nf[0] // world
+        cell = (loc[0].numpy() + np.pi) / (2 * np.pi) * Lz      # local plane coordinate
+        assert cell.min() >= h - 1e-9 and cell.max() < L + h + 1e-9
+        lnf = [Lz, nf[1], nf[2]]
+        grid = oracle.spread([q.numpy() for q in loc[::-1]], src.numpy(), lnf[::-1], ns, beta)
+        local = torch.from_numpy(grid)
+        assert local[:h - 4].abs().max() == 0 and local[Lz - h + 4:].abs().max() == 0  # the safety margin stays empty
+        slab = P.halo_add(local, h)
+        assert slab.shape == (L, nf[1], nf[2])
+        out = P.slab_pencil_fft(slab.contiguous(), nm, nf, iflag, ns, beta, gather=True)
+        want = oracle.nufft1(tuple(nm[::-1]), c, *pts[::-1], iflag=iflag, eps=eps)
+        ret[rank] = oracle.relerr(out.numpy(), want)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nm,iflag", [((16, 10, 12), 1), ((24, 9, 8), -1)])
+def test_slab_split_matches_single_process_oracle(nm, iflag):
+    world = 2
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker_slab, args=(world, _free_port(), nm, 700, iflag, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert ret[r] < 1e-11, dict(ret)
+
+
 def _worker_split(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
