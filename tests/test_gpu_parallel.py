@@ -44,6 +44,52 @@ def test_slab_split_single_gpu(nm, iflag):
     b = J.nufft1(nm, tc, *tp, iflag=iflag, eps=1e-6)
     assert a.shape == b.shape == tuple(nm)
     assert oracle.relerr(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
+    # double precision (tile kernels behind the spread-only plan), eps = 1e-10
+    tp64, tc64 = [p.double() for p in tp], tc.to(torch.complex128)
+    a = P.nufft1_sharded_points(nm, tc64, *tp64, combine="slab", iflag=iflag, eps=1e-10)
+    b = J.nufft1(nm, tc64, *tp64, iflag=iflag, eps=1e-10)
+    assert a.dtype == torch.complex128
+    assert oracle.relerr(a.cpu().numpy(), b.cpu().numpy()) < 2e-10
+
+
+def test_slab_partition_groups_points_by_owner():
+    """b2n_slab_partition (csrc/slab.cu) against the torch restatement in exchange_points_by_slab:
+    same owners, same counts, same re-based coordinates, every point exactly once."""
+    import ctypes as C
+
+    from jax_finufft_b200 import _lib
+    from jax_finufft_b200 import parallel as P
+
+    dev = torch.device("cuda:0")
+    M, nf0, world, ns = 200_003, 96, 4, 7
+    h = P.slab_halo(ns)
+    g = torch.Generator(device=dev).manual_seed(2)
+    pts = [(torch.rand(M, generator=g, device=dev) * 2 - 1) * 3 * np.pi for _ in range(3)]  # beyond one period
+    pts[0][:5] = torch.tensor([-np.pi, np.pi, 0.0, np.pi / 2, -np.pi / 2], device=dev)       # on the slab edges
+    c = torch.complex(torch.arange(M, device=dev, dtype=torch.float32), torch.rand(M, generator=g, device=dev))
+    rows = torch.empty((M, 5), dtype=torch.float32, device=dev)
+    cnt = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    vp = C.c_void_p
+    ier = _lib.lib().b2n_slab_partition(0, vp(torch.cuda.current_stream().cuda_stream), M, vp(pts[0].data_ptr()),
+                                        vp(pts[1].data_ptr()), vp(pts[2].data_ptr()), vp(c.data_ptr()), nf0, world, h,
+                                        vp(rows.data_ptr()), vp(cnt.data_ptr()))
+    assert ier == 0
+    torch.cuda.synchronize()
+    L, Lz = nf0 // world, nf0 // world + 2 * h
+    t = pts[0].double() / (2 * np.pi) + 0.5
+    zf = (t - t.floor()) * nf0
+    owner = (zf / L).floor().long().clamp(0, world - 1)
+    z_in = ((zf - owner * L + h) * (2 * np.pi / Lz) - np.pi).float()
+    counts = cnt[:world].cpu()
+    assert torch.equal(counts, torch.bincount(owner, minlength=world).cpu())
+    orig = rows[:, 3].round().long()                                      # Re c = original index
+    assert torch.equal(torch.sort(orig).values, torch.arange(M, device=dev))
+    edges = torch.cat([torch.zeros(1, dtype=torch.int64), counts.cumsum(0)])
+    blk = torch.bucketize(torch.arange(M), edges[1:], right=True).to(dev)  # owner block of each output row
+    assert torch.equal(blk, owner[orig])
+    assert torch.allclose(rows[:, 0], z_in[orig], rtol=0, atol=1e-6)
+    assert torch.equal(rows[:, 1], pts[1][orig]) and torch.equal(rows[:, 2], pts[2][orig])
+    assert torch.equal(rows[:, 4], c.imag[orig])
 
 
 @pytest.mark.parametrize("nm,iflag", [((24, 20, 16), 1), ((16, 18, 30), -1)])
