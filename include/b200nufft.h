@@ -164,11 +164,12 @@ int b2n_set_setpts_cache(int on);
  * reference shards above its custom call, tests/sharding_test.py:119-194): groups this rank's M
  * points by the rank that owns their fine-grid plane along the slowest axis (p0; rank r owns planes
  * [r*nf0/world, (r+1)*nf0/world)) and re-bases that coordinate to the owner's local grid of
- * nf0/world + 2*halo planes.  rows: [M][5] reals {p0', p1, p2, Re c, Im c} grouped by owner;
- * counts2: 2*world uint64 on the device, [0, world) = rows per owner on return.  world <= 16. */
+ * nf0/world + 2*halo planes.  o0 (re-based p0), o1, o2: real[M]; oc: complex[M] -- each grouped
+ * by owner, same order; counts2: 2*world uint64 on the device, [0, world) = points per owner on
+ * return.  world <= 16. */
 int b2n_slab_partition(int is_double, void *stream, int64_t M, const void *p0, const void *p1,
-                       const void *p2, const void *c, int64_t nf0, int world, int halo, void *rows,
-                       void *counts2);
+                       const void *p2, const void *c, int64_t nf0, int world, int halo, void *o0,
+                       void *o1, void *o2, void *oc, void *counts2);
 
 /* Per-stage device timings (ms) of the most recent b2n_execute / b2n_setpts on this plan when
  * opts.debug != 0: [0] sort, [1] spread, [2] fft, [3] deconvolve/amplify, [4] interp,

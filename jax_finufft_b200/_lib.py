@@ -110,7 +110,7 @@ def lib():
         L.b2n_strerror.restype = C.c_char_p
         L.b2n_cache_clear.restype = None
         L.b2n_set_setpts_cache.argtypes = [ci]
-        L.b2n_slab_partition.argtypes = [ci, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, vp]
+        L.b2n_slab_partition.argtypes = [ci, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, vp, vp, vp, vp]
         L.b2n_set_setpts_cache.restype = ci
         L.b2n_setup_spreader.argtypes = [dbl, dbl, ci, ci, C.POINTER(ci), C.POINTER(dbl)]
         L.b2n_next235beven.argtypes = [i64, i64]

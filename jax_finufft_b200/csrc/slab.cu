@@ -3,15 +3,17 @@
 // done above its custom call, tests/sharding_test.py:119-194).  One pass groups a rank's points
 // by the rank that owns their fine-grid plane along the slowest axis and re-bases that coordinate
 // to the owner's local grid of L + 2*halo planes, so that the unmodified spreader can be used
-// on the receiving side; the grouped rows then travel in ONE all_to_all.
+// on the receiving side; the grouped arrays then travel in four all_to_all calls with the same
+// split sizes (20 bytes per point in total).
 //
-//   row = { z_in, y, x, Re c, Im c }   (5 reals; z_in in [-pi, pi) of the LOCAL grid)
+//   outputs, each grouped by owner (structure of arrays, so that the receiver can hand the
+//   arrays to setpts / execute as they arrive): z_in[M] (in [-pi, pi) of the LOCAL grid), y[M], x[M], c[M]
 //   zf  = fold_rescale(z) in float64   (common.cuh), owner = floor(zf / L)
 //   z_in = (zf - owner * L + halo) * 2 pi / (L + 2 halo) - pi
 //
 // k_slab_count: per-CTA shared-memory histogram of the owners, one global atomic per (CTA, owner).
 // k_slab_scatter: a CTA ranks its points per owner in shared memory, reserves one run per owner
-// with a single global atomic and writes its rows there (order inside an owner's run is free).
+// with a single global atomic and writes its points there (order inside an owner's run is free).
 #include "plan.h"
 
 namespace b2n {
@@ -53,7 +55,9 @@ __global__ void __launch_bounds__(SL_T) k_slab_scatter(int64_t M, const T *__res
                                                         const T *__restrict__ x, const cpx<T> *__restrict__ c, int nf0,
                                                         int L, int world, int halo,
                                                         const unsigned long long *__restrict__ counts,
-                                                        unsigned long long *__restrict__ cursors, T *__restrict__ rows) {
+                                                        unsigned long long *__restrict__ cursors, T *__restrict__ oz,
+                                                        T *__restrict__ oy, T *__restrict__ ox,
+                                                        cpx<T> *__restrict__ oc) {
   __shared__ int cnt[SL_MAXW];
   __shared__ long long base[SL_MAXW];
   if (threadIdx.x < SL_MAXW) cnt[threadIdx.x] = 0;
@@ -86,20 +90,18 @@ __global__ void __launch_bounds__(SL_T) k_slab_scatter(int64_t M, const T *__res
   for (int e = 0; e < SL_E; e++) {
     if (own[e] >= 0) {
       const int64_t i = c0 + e * SL_T + threadIdx.x;
-      T *r = rows + (base[own[e]] + rk[e]) * 5;
-      const cpx<T> cv = c[i];
-      r[0] = zin[e];
-      r[1] = y[i];
-      r[2] = x[i];
-      r[3] = cv.x;
-      r[4] = cv.y;
+      const long long j = base[own[e]] + rk[e];
+      oz[j] = zin[e];
+      oy[j] = y[i];
+      ox[j] = x[i];
+      oc[j] = c[i];
     }
   }
 }
 
 template <typename T>
 static int slab_partition(cudaStream_t st, int64_t M, const void *p0, const void *p1, const void *p2, const void *c,
-                          int64_t nf0, int world, int halo, void *rows, void *counts2) {
+                          int64_t nf0, int world, int halo, void *o0, void *o1, void *o2, void *oc, void *counts2) {
   if (world < 1 || world > SL_MAXW || nf0 % world || M < 0) return B2N_ERR_INVALID_ARGUMENT;
   unsigned long long *cnt = (unsigned long long *)counts2;
   B2N_CUDA_OK(cudaMemsetAsync(cnt, 0, 2 * world * sizeof(unsigned long long), st));
@@ -108,7 +110,7 @@ static int slab_partition(cudaStream_t st, int64_t M, const void *p0, const void
   const unsigned nblk = (unsigned)cdiv(M, SL_T * SL_E);
   k_slab_count<T><<<nblk, SL_T, 0, st>>>(M, (const T *)p0, (int)nf0, L, world, cnt);
   k_slab_scatter<T><<<nblk, SL_T, 0, st>>>(M, (const T *)p0, (const T *)p1, (const T *)p2, (const cpx<T> *)c, (int)nf0, L,
-                                          world, halo, cnt, cnt + world, (T *)rows);
+                                          world, halo, cnt, cnt + world, (T *)o0, (T *)o1, (T *)o2, (cpx<T> *)oc);
   B2N_LAUNCHED(2);
   B2N_LAUNCH_OK();
   return 0;
@@ -117,8 +119,9 @@ static int slab_partition(cudaStream_t st, int64_t M, const void *p0, const void
 }  // namespace b2n
 
 extern "C" int b2n_slab_partition(int is_double, void *stream, int64_t M, const void *p0, const void *p1,
-                                  const void *p2, const void *c, int64_t nf0, int world, int halo, void *rows,
-                                  void *counts2) {
-  return is_double ? b2n::slab_partition<double>((cudaStream_t)stream, M, p0, p1, p2, c, nf0, world, halo, rows, counts2)
-                   : b2n::slab_partition<float>((cudaStream_t)stream, M, p0, p1, p2, c, nf0, world, halo, rows, counts2);
+                                  const void *p2, const void *c, int64_t nf0, int world, int halo, void *o0,
+                                  void *o1, void *o2, void *oc, void *counts2) {
+  return is_double
+             ? b2n::slab_partition<double>((cudaStream_t)stream, M, p0, p1, p2, c, nf0, world, halo, o0, o1, o2, oc, counts2)
+             : b2n::slab_partition<float>((cudaStream_t)stream, M, p0, p1, p2, c, nf0, world, halo, o0, o1, o2, oc, counts2);
 }

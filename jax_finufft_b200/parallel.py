@@ -292,18 +292,29 @@ def exchange_points_by_slab(source_local, points_local, nf0, ns, group=None):
         cdt = torch.complex64 if rdt == torch.float32 else torch.complex128
         pp = [q.to(rdt).contiguous() for q in points_local]
         cc = source_local.to(cdt).contiguous()
-        rows = torch.empty((M, 5), dtype=rdt, device=z.device)
+        outs = [torch.empty(M, dtype=rdt, device=z.device) for _ in range(3)] + [torch.empty(M, dtype=cdt, device=z.device)]
         cnt = torch.empty(2 * world, dtype=torch.int64, device=z.device)
         vp = C.c_void_p
         ier = _lib.lib().b2n_slab_partition(int(rdt == torch.float64), vp(torch.cuda.current_stream(z.device).cuda_stream),
                                             M, vp(pp[0].data_ptr()), vp(pp[1].data_ptr()), vp(pp[2].data_ptr()),
-                                            vp(cc.data_ptr()), int(nf0), world, h, vp(rows.data_ptr()), vp(cnt.data_ptr()))
+                                            vp(cc.data_ptr()), int(nf0), world, h, *[vp(o.data_ptr()) for o in outs],
+                                            vp(cnt.data_ptr()))
         if ier:
             raise RuntimeError(f"b2n_slab_partition failed with code {ier}")
-        if world > 1:
-            rows = _rows_all_to_all(rows, cnt[:world], group)
-        pts = [rows[:, d].contiguous() for d in range(3)]
-        return torch.complex(rows[:, 3].contiguous(), rows[:, 4].contiguous()), pts, Lz
+        if world > 1:  # the arrays travel as they are (structure of arrays): nothing to unpack on arrival
+            send = cnt[:world]
+            got = torch.empty_like(send)
+            dist.all_to_all_single(got, send, group=group)
+            sent, got = torch.stack([send, got]).tolist()  # the one host read of this path: the split sizes
+            recv = []
+            for o in outs:
+                flat = torch.view_as_real(o) if o.is_complex() else o
+                w = 2 if o.is_complex() else 1
+                r = torch.empty((sum(got),) + tuple(flat.shape[1:]), dtype=flat.dtype, device=z.device)
+                dist.all_to_all_single(r, flat, output_split_sizes=got, input_split_sizes=sent, group=group)
+                recv.append(torch.view_as_complex(r) if w == 2 else r)
+            outs = recv
+        return outs[3], outs[:3], Lz
     two_pi = 2.0 * np.pi
     t = z.to(torch.float64) / two_pi + 0.5
     zf = (t - torch.floor(t)) * float(nf0)                       # fold_rescale (csrc/common.cuh), in float64

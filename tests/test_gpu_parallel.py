@@ -67,12 +67,14 @@ def test_slab_partition_groups_points_by_owner():
     pts = [(torch.rand(M, generator=g, device=dev) * 2 - 1) * 3 * np.pi for _ in range(3)]  # beyond one period
     pts[0][:5] = torch.tensor([-np.pi, np.pi, 0.0, np.pi / 2, -np.pi / 2], device=dev)       # on the slab edges
     c = torch.complex(torch.arange(M, device=dev, dtype=torch.float32), torch.rand(M, generator=g, device=dev))
-    rows = torch.empty((M, 5), dtype=torch.float32, device=dev)
+    oz, oy, ox = (torch.empty(M, dtype=torch.float32, device=dev) for _ in range(3))
+    oc = torch.empty(M, dtype=torch.complex64, device=dev)
     cnt = torch.empty(2 * world, dtype=torch.int64, device=dev)
     vp = C.c_void_p
     ier = _lib.lib().b2n_slab_partition(0, vp(torch.cuda.current_stream().cuda_stream), M, vp(pts[0].data_ptr()),
                                         vp(pts[1].data_ptr()), vp(pts[2].data_ptr()), vp(c.data_ptr()), nf0, world, h,
-                                        vp(rows.data_ptr()), vp(cnt.data_ptr()))
+                                        vp(oz.data_ptr()), vp(oy.data_ptr()), vp(ox.data_ptr()), vp(oc.data_ptr()),
+                                        vp(cnt.data_ptr()))
     assert ier == 0
     torch.cuda.synchronize()
     L, Lz = nf0 // world, nf0 // world + 2 * h
@@ -82,14 +84,14 @@ def test_slab_partition_groups_points_by_owner():
     z_in = ((zf - owner * L + h) * (2 * np.pi / Lz) - np.pi).float()
     counts = cnt[:world].cpu()
     assert torch.equal(counts, torch.bincount(owner, minlength=world).cpu())
-    orig = rows[:, 3].round().long()                                      # Re c = original index
+    orig = oc.real.round().long()                                          # Re c = original index
     assert torch.equal(torch.sort(orig).values, torch.arange(M, device=dev))
     edges = torch.cat([torch.zeros(1, dtype=torch.int64), counts.cumsum(0)])
     blk = torch.bucketize(torch.arange(M), edges[1:], right=True).to(dev)  # owner block of each output row
     assert torch.equal(blk, owner[orig])
-    assert torch.allclose(rows[:, 0], z_in[orig], rtol=0, atol=1e-6)
-    assert torch.equal(rows[:, 1], pts[1][orig]) and torch.equal(rows[:, 2], pts[2][orig])
-    assert torch.equal(rows[:, 4], c.imag[orig])
+    assert torch.allclose(oz, z_in[orig], rtol=0, atol=1e-6)
+    assert torch.equal(oy, pts[1][orig]) and torch.equal(ox, pts[2][orig])
+    assert torch.equal(oc.imag, c.imag[orig])
 
 
 @pytest.mark.parametrize("nm,iflag", [((24, 20, 16), 1), ((16, 18, 30), -1)])
