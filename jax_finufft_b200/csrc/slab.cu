@@ -25,7 +25,7 @@ __device__ __forceinline__ int slab_owner(T z, int nf0, int L, int world, double
   double t = fma((double)z, 0.159154943091895345554011992339482617, 0.5);
   t -= floor(t);
   const double zf = t * (double)nf0;
-  int o = (int)(zf / (double)L);
+  int o = (int)(zf * (1.0 / (double)L));  // any consistent choice on a slab edge is fine: the halo covers both sides
   o = o < 0 ? 0 : (o >= world ? world - 1 : o);
   *zf_out = zf;
   return o;

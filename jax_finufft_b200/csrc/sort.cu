@@ -624,17 +624,39 @@ __device__ __forceinline__ unsigned long long sig_bits(float v) { return (unsign
 __device__ __forceinline__ unsigned long long sig_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
 
 template <typename T>
+__device__ __forceinline__ unsigned long long sig_point(int dim, int64_t i, T x, T y, T z) {
+  unsigned long long v = sig_mix(sig_bits(x) + 0x9e3779b97f4a7c15ull * (unsigned long long)(i + 1));
+  if (dim > 1) v = sig_mix(v ^ sig_bits(y));
+  if (dim > 2) v = sig_mix(v ^ (sig_bits(z) << 1));
+  return v;
+}
+// VEC: the arrays are 16-byte aligned -- four (float) or two (double) points per load.  The sum is
+// commutative, so both variants give the same signature.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) k_pts_signature(int dim, int64_t M, const T *__restrict__ x,
                                                         const T *__restrict__ y, const T *__restrict__ z,
                                                         unsigned long long *__restrict__ acc) {
   __shared__ unsigned long long part[8];
   unsigned long long h = 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
-    unsigned long long v = sig_mix(sig_bits(x[i]) + 0x9e3779b97f4a7c15ull * (unsigned long long)(i + 1));
-    if (dim > 1) v = sig_mix(v ^ sig_bits(y[i]));
-    if (dim > 2) v = sig_mix(v ^ (sig_bits(z[i]) << 1));
-    h += v;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (VEC) {
+    constexpr int W = 16 / sizeof(T);
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    const int64_t nv = M / W;
+    for (int64_t j = tid; j < nv; j += stride) {
+      T a[W], b[W], c[W];
+      *reinterpret_cast<V *>(a) = __ldcs(reinterpret_cast<const V *>(x) + j);
+      if (dim > 1) *reinterpret_cast<V *>(b) = __ldcs(reinterpret_cast<const V *>(y) + j);
+      if (dim > 2) *reinterpret_cast<V *>(c) = __ldcs(reinterpret_cast<const V *>(z) + j);
+#pragma unroll
+      for (int k = 0; k < W; k++) h += sig_point<T>(dim, j * W + k, a[k], dim > 1 ? b[k] : T(0), dim > 2 ? c[k] : T(0));
+    }
+    for (int64_t i = nv * W + tid; i < M; i += stride)
+      h += sig_point<T>(dim, i, x[i], dim > 1 ? y[i] : T(0), dim > 2 ? z[i] : T(0));
+  } else {
+    for (int64_t i = tid; i < M; i += stride)
+      h += sig_point<T>(dim, i, x[i], dim > 1 ? y[i] : T(0), dim > 2 ? z[i] : T(0));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
@@ -701,7 +723,9 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     for (int w : gw) salt = (salt ^ (unsigned long long)(unsigned)w) * 0x100000001b3ull;
     const int allow = was_ok && ps.sig_salt == salt;
     ps.sig_salt = salt;
-    k_pts_signature<T><<<148 * 8, 256, 0, st>>>(g.dim, M, x, y, z, ps.sig);
+    const bool vec = (((uintptr_t)x | (g.dim > 1 ? (uintptr_t)y : 0) | (g.dim > 2 ? (uintptr_t)z : 0)) & 15) == 0;
+    if (vec) k_pts_signature<T, true><<<148 * 8, 256, 0, st>>>(g.dim, M, x, y, z, ps.sig);
+    else k_pts_signature<T, false><<<148 * 8, 256, 0, st>>>(g.dim, M, x, y, z, ps.sig);
     k_sig_decide<<<1, 1, 0, st>>>(ps.sig, salt, allow);
     B2N_LAUNCHED(2);
     B2N_LAUNCH_OK();

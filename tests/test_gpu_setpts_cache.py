@@ -86,6 +86,16 @@ def test_cache_on_equals_cache_off(cache_on, ndim, nm, M, x64, eps):
     assert relerr(J.nufft1(nm, c, *pts, eps=eps), ref["a"]) < tol
     assert relerr(J.nufft1(nm, c_s, *pts_s, eps=eps), ref["s"]) < tol    # other M
     assert relerr(J.nufft1(nm, c, *pts, eps=eps), ref["a"]) < tol
+    # same coordinates in arrays that are not 16-byte aligned (scalar signature kernel; the sum is
+    # commutative, so the signature -- and the cache hit -- is the same)
+    mis = []
+    for q in pts:
+        buf = torch.empty(M + 1, dtype=q.dtype, device=DEV)
+        buf[1:].copy_(q)
+        mis.append(buf[1:])
+    assert mis[0].data_ptr() % 16 != 0
+    for k in range(2):
+        assert relerr(J.nufft1(nm, c, *mis, eps=eps), ref["a"]) < tol, k
     # type 2 has its own cached plan (and its own sorted copy)
     for k in range(2):
         assert relerr(J.nufft2(f2, *pts, eps=eps), ref["a2"]) < tol, k
