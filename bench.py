@@ -125,6 +125,10 @@ def cpu_port_rate(typ, M_full, nm, eps, sample, steps, warmup):
     between the two, extrapolated linearly in M to the full workload."""
     import oracle
 
+    try:  # all the host cores this process may use, whatever OMP_NUM_THREADS the launcher exported
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        oracle.set_num_threads(os.cpu_count() or 1)
     rng = np.random.default_rng(1)
     x = rng.uniform(-np.pi, np.pi, size=(3, sample))
     nmx = tuple(nm[::-1])

@@ -271,6 +271,11 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP threads of the C restatement (launchers such as torchrun export OMP_NUM_THREADS=1)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+
+
 def relerr(a, b):
     """relative l2 error ||a-b||/||b|| in float64 (V/test/utils/norms.hpp:15-37)."""
     a = np.asarray(a, dtype=np.complex128).ravel()

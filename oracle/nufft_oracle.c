@@ -805,6 +805,15 @@ void orc_dirft3(int dim, long M, const double *x, const double *y, const double 
   }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline uses every core it is given */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
