@@ -58,6 +58,11 @@ namespace b2n {
 #ifndef SWR_S
 #define SWR_S 3
 #endif
+// 1: class-specialised spread loops (points of a batch ordered by (plane, y class); the row slot a
+// class never touches is not computed): type-1 step 12.46 -> 12.26 ms at C3.  0 rebuilds the plain chain.
+#ifndef SWR_YCLASS
+#define SWR_YCLASS 1
+#endif
 #ifndef SWR_BZ_N
 #define SWR_BZ_N 64
 #endif
@@ -156,7 +161,7 @@ __device__ __forceinline__ bool swr_decode(const SwrArgs &a, int sp, int &first,
 // pr4 = the point record; cv = strength (spread) or (1, 1) (interp: the x row holds (kx, kx))
 template <int NS>
 __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const float4 pr4, float2 cv,
-                                            int xa, int ya, float *row) {
+                                            int xa, int ya, float *row, int meta_shift = 0, int meta_cls = 0) {
   using C = SwrCfg<NS>;
   constexpr int NP = C::NP;
   const float px = pr4.x, py = pr4.y, pz = pr4.z;
@@ -218,7 +223,7 @@ __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const
     float kzm[C::KZW];
 #pragma unroll
     for (int j = 0; j < C::KZW; j++) kzm[j] = j < NS ? kz[j] : 0.f;
-    kzm[C::KZW - 1] = __int_as_float(isz);
+    kzm[C::KZW - 1] = __int_as_float((isz << meta_shift) + meta_cls);
 #pragma unroll
     for (int i = 0; i < C::KZW / 4; i++)
       *reinterpret_cast<float4 *>(row + C::KZO + 4 * i) = make_float4(kzm[4 * i], kzm[4 * i + 1], kzm[4 * i + 2], kzm[4 * i + 3]);
@@ -315,11 +320,15 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
   SwrRow<NS> pr;
   const float *myx = rows + C::KXO + 2 * CX * q;
   const float *myy = rows + C::KYO + 4 * r;
-  auto point = [&](auto phc, int ron) {
+  // CLS (SWR_YCLASS builds): 0 = the point's y window ends below row slot S-1, 2 = it starts above
+  // row slot 0, 1 = anything: the untouched slot's FMUL2 + D FFMA2 are not issued at all
+  auto point = [&](auto phc, auto clc, int ron) {
     constexpr int PH = decltype(phc)::value;
+    constexpr int CLS = decltype(clc)::value;
+    constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
     float2 wv[S][CX];
 #pragma unroll
-    for (int s = 0; s < S; s++)
+    for (int s = S0; s < S1; s++)
 #pragma unroll
       for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
     pr.load_xy(myx, myy, ron);
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
         if (j < D) {
           const float2 kzj = pr.kz(j);
 #pragma unroll
-          for (int s = 0; s < S; s++)
+          for (int s = S0; s < S1; s++)
 #pragma unroll
             for (int c = 0; c < CX; c++)
               acc[s][c][(PH + j) % D] = fma2(wv[s][c], kzj, acc[s][c][(PH + j) % D]);
@@ -366,11 +375,40 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
     const float2 cB = b0 + C::PB + lane < cnt ? ldc(recB, sB) : zero2;
     __syncwarp();
+#if SWR_YCLASS
+    // order the batch by (window plane, y class) so that the phase chain can run class-specialised
+    // loops: the batch arrives ordered by plane, so only runs of equal planes are permuted
+    int pos = lane, cls = 1;
+    if constexpr (S == 3) {
+      const bool act = lane < nb;
+      const int isz = act ? window_start(recA.z, NS) : 0x3fffffff - lane;
+      int yl = window_start(recA.y, NS) - ya;
+      yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
+      const int prev = __shfl_up_sync(0xffffffffu, isz, 1);
+      const bool sorted = !__any_sync(0xffffffffu, act && lane > 0 && isz < prev);
+      if (sorted) {
+        cls = yl + NS <= 4 * (S - 1) ? 0 : (yl >= 4 ? 2 : 1);
+        const unsigned peers = __match_any_sync(0xffffffffu, isz);
+        const unsigned b0 = __ballot_sync(0xffffffffu, act && cls == 0) & peers;
+        const unsigned b1 = __ballot_sync(0xffffffffu, act && cls == 1) & peers;
+        const unsigned b2 = __ballot_sync(0xffffffffu, act && cls == 2) & peers;
+        const unsigned lt = (1u << lane) - 1u;
+        const int rank = cls == 0 ? __popc(b0 & lt) : (cls == 1 ? __popc(b0) + __popc(b1 & lt) : __popc(b0) + __popc(b1) + __popc(b2 & lt));
+        pos = __ffs(peers) - 1 + rank;
+      }
+    }
+    if (lane < nb) {
+      float2 cv = cA;
+      if (a.scale) cv = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
+      swr_weights<NS>(tab, recA, cv, xa, ya, rows + pos * C::ROW, 2, cls);
+    }
+#else
     if (lane < nb) {
       float2 cv = cA;
       if (a.scale) cv = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
       swr_weights<NS>(tab, recA, cv, xa, ya, rows + lane * C::ROW);
     }
+#endif
     __syncwarp();
     recA = recB;
     recB = recC;
@@ -380,21 +418,40 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     pr.load_xy(myx, myy, 0);
 #pragma unroll
     for (int i = 0; i < SwrRow<NS>::NV; i++) pr.load_kv(rows, 0, i);
+#if SWR_YCLASS
+#define SWR_ZP(m) ((m) >> 2) /* META = plane * 4 + class */
+#define SWR_SPREAD_POINTS(PH)                                                                   \
+      SWR_SPREAD_CLASS(PH, 0)                                                                   \
+      SWR_SPREAD_CLASS(PH, 1)                                                                   \
+      SWR_SPREAD_CLASS(PH, 2)
+#define SWR_SPREAD_CLASS(PH, CL)                                                                \
+      while (t < nb && zw == 4 * cur + CL) {                                                    \
+        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
+        point(std::integral_constant<int, PH>{}, std::integral_constant<int, CL>{}, ron);       \
+        t++;                                                                                    \
+        ro = ron;                                                                               \
+        zw = pr.zw();                                                                           \
+      }
+#else
+#define SWR_ZP(m) (m)
+#define SWR_SPREAD_POINTS(PH)                                                                   \
+      while (t < nb && zw == cur) {                                                             \
+        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
+        point(std::integral_constant<int, PH>{}, std::integral_constant<int, 1>{}, ron);        \
+        t++;                                                                                    \
+        ro = ron;                                                                               \
+        zw = pr.zw();                                                                           \
+      }
+#endif
     int zw = pr.zw();
-    if (cur == SWR_EMPTY) cur = zw;  // first point: ring empty, ph = 0
+    if (cur == SWR_EMPTY) cur = SWR_ZP(zw);  // first point: ring empty, ph = 0
   reenter:
     for (;;) {
       switch (ph) {
 #define SWR_SPREAD_PHASE(PH)                                                                    \
   case PH:                                                                                      \
     if constexpr (PH < D) {                                                                     \
-      while (t < nb && zw == cur) {                                                             \
-        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
-        point(std::integral_constant<int, PH>{}, ron);                                          \
-        t++;                                                                                    \
-        ro = ron;                                                                               \
-        zw = pr.zw();                                                                           \
-      }                                                                                         \
+      SWR_SPREAD_POINTS(PH)                                                                     \
       if (t >= nb && !last) {                                                                   \
         ph = PH;                                                                                \
         goto batch_done;                                                                        \
@@ -404,11 +461,11 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
       if (drain) {                                                                              \
         if (--drain == 0) {                                                                     \
           if (t >= nb) goto sub_done;                                                           \
-          cur = zw; /* ring is empty: re-base the phases on the next point's window */          \
+          cur = SWR_ZP(zw); /* ring is empty: re-base the phases on the next point's window */  \
           ph = 0;                                                                               \
           goto reenter;                                                                         \
         }                                                                                       \
-      } else if (t >= nb || (unsigned)(zw - cur + 1) >= (unsigned)D) {                          \
+      } else if (t >= nb || (unsigned)(SWR_ZP(zw) - cur + 1) >= (unsigned)D) {                  \
         drain = D - 1; /* end of the subproblem, or a gap wider than the ring */                \
       }                                                                                         \
     }
@@ -421,6 +478,9 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
         SWR_SPREAD_PHASE(6)
         SWR_SPREAD_PHASE(7)
 #undef SWR_SPREAD_PHASE
+#undef SWR_SPREAD_POINTS
+#undef SWR_SPREAD_CLASS
+#undef SWR_ZP
         default: break;
       }
       ph = 0;
