@@ -63,6 +63,9 @@ namespace b2n {
 #ifndef SWR_YCLASS
 #define SWR_YCLASS 1
 #endif
+#ifndef SWR_YCLASS_INTERP
+#define SWR_YCLASS_INTERP 0
+#endif
 #ifndef SWR_BZ_N
 #define SWR_BZ_N 64
 #endif
@@ -230,6 +233,37 @@ __device__ __forceinline__ void swr_weights(const HornerTable<float> &tab, const
   }
 }
 
+// Position and y class of lane's point inside its batch of nb points, for the class-specialised
+// loops: the batch arrives ordered by window plane, so only runs of equal planes are permuted
+// (class 0 first).  Class 0: the y window ends below row slot S-1; class 2: it starts above row
+// slot 0; class 1: anything.  A batch that is not ordered by plane (periodic seam) keeps its order
+// and is all class 1.
+template <int NS>
+__device__ __forceinline__ void swr_batch_order(const float4 &rec, int nb, int ya, int lane, int &pos, int &cls) {
+  using C = SwrCfg<NS>;
+  pos = lane;
+  cls = 1;
+  if constexpr (C::S == 3) {
+    const bool act = lane < nb;
+    const int isz = act ? window_start(rec.z, NS) : 0x3fffffff - lane;
+    int yl = window_start(rec.y, NS) - ya;
+    yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
+    const int prev = __shfl_up_sync(0xffffffffu, isz, 1);
+    const bool sorted = !__any_sync(0xffffffffu, act && lane > 0 && isz < prev);
+    if (sorted) {
+      cls = yl + NS <= 4 * (C::S - 1) ? 0 : (yl >= 4 ? 2 : 1);
+      const unsigned peers = __match_any_sync(0xffffffffu, isz);
+      const unsigned b0 = __ballot_sync(0xffffffffu, act && cls == 0) & peers;
+      const unsigned b1 = __ballot_sync(0xffffffffu, act && cls == 1) & peers;
+      const unsigned b2 = __ballot_sync(0xffffffffu, act && cls == 2) & peers;
+      const unsigned lt = (1u << lane) - 1u;
+      const int rank = cls == 0 ? __popc(b0 & lt)
+                                : (cls == 1 ? __popc(b0) + __popc(b1 & lt) : __popc(b0) + __popc(b1) + __popc(b2 & lt));
+      pos = __ffs(peers) - 1 + rank;
+    }
+  }
+}
+
 // One point's weights as the inner loop holds them in registers: this lane's x weight(s), its
 // y weights, the (kz, kz) pairs in plane order and the window's first plane (META).  The loops
 // below keep ONE such set live and reload each piece from the NEXT point's row right after its
@@ -376,27 +410,9 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     const float2 cB = b0 + C::PB + lane < cnt ? ldc(recB, sB) : zero2;
     __syncwarp();
 #if SWR_YCLASS
-    // order the batch by (window plane, y class) so that the phase chain can run class-specialised
-    // loops: the batch arrives ordered by plane, so only runs of equal planes are permuted
-    int pos = lane, cls = 1;
-    if constexpr (S == 3) {
-      const bool act = lane < nb;
-      const int isz = act ? window_start(recA.z, NS) : 0x3fffffff - lane;
-      int yl = window_start(recA.y, NS) - ya;
-      yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
-      const int prev = __shfl_up_sync(0xffffffffu, isz, 1);
-      const bool sorted = !__any_sync(0xffffffffu, act && lane > 0 && isz < prev);
-      if (sorted) {
-        cls = yl + NS <= 4 * (S - 1) ? 0 : (yl >= 4 ? 2 : 1);
-        const unsigned peers = __match_any_sync(0xffffffffu, isz);
-        const unsigned b0 = __ballot_sync(0xffffffffu, act && cls == 0) & peers;
-        const unsigned b1 = __ballot_sync(0xffffffffu, act && cls == 1) & peers;
-        const unsigned b2 = __ballot_sync(0xffffffffu, act && cls == 2) & peers;
-        const unsigned lt = (1u << lane) - 1u;
-        const int rank = cls == 0 ? __popc(b0 & lt) : (cls == 1 ? __popc(b0) + __popc(b1 & lt) : __popc(b0) + __popc(b1) + __popc(b2 & lt));
-        pos = __ffs(peers) - 1 + rank;
-      }
-    }
+    // order the batch by (window plane, y class) so that the phase chain can run class-specialised loops
+    int pos, cls;
+    swr_batch_order<NS>(recA, nb, ya, lane, pos, cls);
     if (lane < nb) {
       float2 cv = cA;
       if (a.scale) cv = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
@@ -560,11 +576,13 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
   SwrRow<NS> pr;
   const float *myx = rows + C::KXO + 2 * CX * q;
   const float *myy = rows + C::KYO + 4 * r;
-  auto point = [&](auto phc, int ron) {
+  auto point = [&](auto phc, auto clc, int ron) {
     constexpr int PH = decltype(phc)::value;
+    constexpr int CLS = decltype(clc)::value;  // see swr_batch_order: the row slot a class never touches is skipped
+    constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
     float2 wv[S][CX];
 #pragma unroll
-    for (int s = 0; s < S; s++)
+    for (int s = S0; s < S1; s++)
 #pragma unroll
       for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
     pr.load_xy(myx, myy, ron);
@@ -576,7 +594,7 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
         if (j < D) {
           const float2 kzj = pr.kz(j);
 #pragma unroll
-          for (int s = 0; s < S; s++)
+          for (int s = S0; s < S1; s++)
 #pragma unroll
             for (int c = 0; c < CX; c++)
               part[s][c] = j == 0 ? mul2(val[s][c][(PH + j) % D], kzj)
@@ -585,12 +603,12 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
       }
       pr.load_kv(rows, ron, i);
     }
-    float2 res = mul2(part[0][0], wv[0][0]);
+    float2 res = mul2(part[S0][0], wv[S0][0]);
 #pragma unroll
-    for (int s = 0; s < S; s++)
+    for (int s = S0; s < S1; s++)
 #pragma unroll
       for (int c = 0; c < CX; c++)
-        if (s + c > 0) res = fma2(part[s][c], wv[s][c], res);
+        if (s - S0 + c > 0) res = fma2(part[s][c], wv[s][c], res);
     return res;
   };
 
@@ -602,16 +620,56 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
   for (int b0 = 0; b0 < cnt; b0 += C::PB) {
     const int nb = min(C::PB, cnt - b0);
     const float4 recB = b0 + C::PB + lane < cnt ? ld_stream4(recp + b0 + C::PB) : zrec;
-    const int orig = __float_as_int(recA.w);
-    float2 mine = make_float2(0.f, 0.f);  // interpolated value of point b0 + lane
+    float2 mine = make_float2(0.f, 0.f);  // interpolated value of the point at batch position `lane`
     __syncwarp();
+#if SWR_YCLASS_INTERP
+    int pos, cls;
+    swr_batch_order<NS>(recA, nb, ya, lane, pos, cls);
+    // original index by batch POSITION, parked in the pad column of RES (never read or written by the sums)
+    int *opad = reinterpret_cast<int *>(RES + 32);
+    if (lane < nb) {
+      opad[(pos & 15) * 66 + (pos >> 4)] = __float_as_int(recA.w);
+      swr_weights<NS>(tab, recA, make_float2(1.f, 1.f), xa, ya, rows + pos * C::ROW, 2, cls);
+    }
+    __syncwarp();
+    const int orig = lane < nb ? opad[(lane & 15) * 66 + (lane >> 4)] : 0;
+#else
+    const int orig = __float_as_int(recA.w);
     if (lane < nb) swr_weights<NS>(tab, recA, make_float2(1.f, 1.f), xa, ya, rows + lane * C::ROW);
     __syncwarp();
+#endif
     recA = recB;
     int t = 0, ro = 0;
     pr.load_xy(myx, myy, 0);
 #pragma unroll
     for (int i = 0; i < SwrRow<NS>::NV; i++) pr.load_kv(rows, 0, i);
+#if SWR_YCLASS_INTERP
+#define SWR_ZP(m) ((m) >> 2) /* META = plane * 4 + class */
+#define SWR_INTERP_POINTS(PH)                                                                   \
+      SWR_INTERP_CLASS(PH, 0)                                                                   \
+      SWR_INTERP_CLASS(PH, 1)                                                                   \
+      SWR_INTERP_CLASS(PH, 2)
+#define SWR_INTERP_CLASS(PH, CL)                                                                \
+      while (t < tend && zw == 4 * cur + CL) {                                                  \
+        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
+        *rw = point(std::integral_constant<int, PH>{}, std::integral_constant<int, CL>{}, ron); \
+        rw += 33;                                                                               \
+        t++;                                                                                    \
+        ro = ron;                                                                               \
+        zw = pr.zw();                                                                           \
+      }
+#else
+#define SWR_ZP(m) (m)
+#define SWR_INTERP_POINTS(PH)                                                                   \
+      while (t < tend && zw == cur) {                                                           \
+        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
+        *rw = point(std::integral_constant<int, PH>{}, std::integral_constant<int, 1>{}, ron);  \
+        rw += 33;                                                                               \
+        t++;                                                                                    \
+        ro = ron;                                                                               \
+        zw = pr.zw();                                                                           \
+      }
+#endif
     int zw = pr.zw();
     bool fill = cur == SWR_EMPTY;
     for (int half = 0; half * 16 < nb; half++) {
@@ -619,7 +677,7 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
       float2 *rw = res_w;
     reenter:
       if (fill) {  // first point, or a gap wider than the ring (or disorder): one shared copy
-        cur = zw;
+        cur = SWR_ZP(zw);
         refill(cur);
         ph = 0;
         fill = false;
@@ -629,19 +687,12 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
 #define SWR_INTERP_PHASE(PH)                                                                    \
   case PH:                                                                                      \
     if constexpr (PH < D) {                                                                     \
-      while (t < tend && zw == cur) {                                                           \
-        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
-        *rw = point(std::integral_constant<int, PH>{}, ron);                                    \
-        rw += 33;                                                                               \
-        t++;                                                                                    \
-        ro = ron;                                                                               \
-        zw = pr.zw();                                                                           \
-      }                                                                                         \
+      SWR_INTERP_POINTS(PH)                                                                     \
       if (t >= tend) {                                                                          \
         ph = PH;                                                                                \
         goto half_done;                                                                         \
       }                                                                                         \
-      if ((unsigned)(zw - cur) >= (unsigned)D) {                                                \
+      if ((unsigned)(SWR_ZP(zw) - cur) >= (unsigned)D) {                                        \
         fill = true;                                                                            \
         goto reenter;                                                                           \
       }                                                                                         \
@@ -660,6 +711,9 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
           SWR_INTERP_PHASE(6)
           SWR_INTERP_PHASE(7)
 #undef SWR_INTERP_PHASE
+#undef SWR_INTERP_POINTS
+#undef SWR_INTERP_CLASS
+#undef SWR_ZP
           default: break;
         }
         ph = 0;
