@@ -1,142 +1,122 @@
-"""Tuning options -- host-side mirror of ``src/jax_finufft/options.py`` (reference file:line cited
-per item).  Same names, defaults and resolution rules; only the seven GPU fields that the
-reference forwards across its FFI boundary (options.py:105-119, lowering.py:157-174) reach the
-backend, exactly as upstream.  CPU-only fields are accepted and ignored (there is no CPU path).
+"""Tuning options: the ``opts`` argument of ``nufft1/2/3``.
+
+Host-side mirror of the reference's option structs (``src/jax_finufft/options.py``): the same
+class names, field names, defaults and resolution rule, so that user code written against
+jax-finufft (``Opts(gpu_method=..., modeord=...)``, ``NestedOpts(type1=..., backward=...)``) keeps
+working.  The implementation is table-driven: one table lists every field with its default, its
+validation rule and whether it crosses the custom-call boundary.  Only seven GPU fields do
+(options.py:105-119, lowering.py:157-174); the CPU-only fields are accepted and ignored -- there is
+no CPU path in this backend.
 """
 
-from dataclasses import dataclass
+import dataclasses
 from enum import IntEnum
-from typing import Optional, Union
+from types import SimpleNamespace
 
 __all__ = ["Opts", "NestedOpts", "unpack_opts", "DebugLevel", "GpuDebugLevel", "GpuMethod",
            "SpreadSort", "SpreadThread", "FftwFlags"]
 
+# ------------------------------------------------------------------------------------------ enums
+# (options.py:9-43).  FftwFlags: upstream reads these integers from its CPU extension module
+# (FFTW's public flag values); there is no FFTW here, the enum only keeps `Opts(fftw=...)` call
+# sites working.  GpuMethod additionally names the reference library's method 3.
+DebugLevel = IntEnum("DebugLevel", {"Silent": 0, "Verbose": 1, "Noisy": 2})
+GpuDebugLevel = IntEnum("GpuDebugLevel", {"Silent": 0, "Verbose": 1})
+SpreadSort = IntEnum("SpreadSort", {"NoSort": 0, "Sort": 1, "Heuristic": 2})
+SpreadThread = IntEnum("SpreadThread", {"Auto": 0, "Sequential": 1, "Parallel": 2})
+GpuMethod = IntEnum("GpuMethod", {"Auto": 0, "Driven": 1, "Shared": 2, "OutputDriven": 3})
+FftwFlags = IntEnum("FftwFlags", {"Estimate": 1 << 6, "Measure": 0, "Patient": 1 << 5, "Exhaustive": 1 << 3,
+                                  "WisdomOnly": 1 << 21})
+for _e in (DebugLevel, GpuDebugLevel, SpreadSort, SpreadThread, GpuMethod, FftwFlags):
+    _e.__module__ = __name__
 
-class DebugLevel(IntEnum):  # options.py:9-12
-    Silent = 0
-    Verbose = 1
-    Noisy = 2
+# ----------------------------------------------------------------------------------------- fields
+# name, default, rule, name of the attribute it becomes on the custom call (None: stays on the host)
+_FLAG = "flag"          # bool (or 0 / 1)
+_ANY = None             # not validated: ignored by this backend
+_FIELDS = (
+    # CPU FINUFFT fields of the reference struct (options.py:50-63)
+    ("modeord", False, _FLAG, "modeord"),
+    ("debug", DebugLevel.Silent, _ANY, None),
+    ("spread_debug", DebugLevel.Silent, _ANY, None),
+    ("showwarn", False, _ANY, None),
+    ("nthreads", 0, _ANY, None),
+    ("fftw", FftwFlags.Estimate, _ANY, None),
+    ("spread_sort", SpreadSort.Heuristic, _ANY, None),
+    ("spread_kerevalmeth", True, _ANY, None),
+    ("spread_kerpad", True, _ANY, None),
+    ("upsampfac", 0.0, _ANY, None),
+    ("spread_thread", SpreadThread.Auto, _ANY, None),
+    ("maxbatchsize", 0, _ANY, None),
+    ("spread_nthr_atomic", -1, _ANY, None),
+    ("spread_max_sp_size", 0, _ANY, None),
+    # GPU fields (options.py:65-78); defaults of V/src/cuda/cufinufft.cu:133-152
+    ("gpu_upsampfac", 2.0, _ANY, "upsampfac"),
+    ("gpu_method", 0, (0, 1, 2, 3), "gpu_method"),
+    ("gpu_sort", True, _FLAG, "gpu_sort"),
+    ("gpu_binsizex", 0, _ANY, None),
+    ("gpu_binsizey", 0, _ANY, None),
+    ("gpu_binsizez", 0, _ANY, None),
+    ("gpu_obinsizex", 0, _ANY, None),
+    ("gpu_obinsizey", 0, _ANY, None),
+    ("gpu_obinsizez", 0, _ANY, None),
+    ("gpu_maxsubprobsize", 1024, _ANY, None),
+    ("gpu_kerevalmeth", True, _FLAG, "gpu_kerevalmeth"),
+    ("gpu_spreadinterponly", False, _FLAG, None),
+    ("gpu_maxbatchsize", 0, "nonneg", "gpu_maxbatchsize"),
+    ("gpu_debug", GpuDebugLevel.Silent, (0, 1), "debug"),
+)
 
 
-class GpuDebugLevel(IntEnum):  # options.py:15-17
-    Silent = 0
-    Verbose = 1
-
-
-class FftwFlags(IntEnum):
-    # options.py:20-25 reads these ints from the CPU extension (FFTW's public flag values);
-    # there is no FFTW here, the enum only keeps `Opts(fftw=...)` call sites working.
-    Estimate = 1 << 6
-    Measure = 0
-    Patient = 1 << 5
-    Exhaustive = 1 << 3
-    WisdomOnly = 1 << 21
-
-
-class SpreadSort(IntEnum):  # options.py:28-31
-    NoSort = 0
-    Sort = 1
-    Heuristic = 2
-
-
-class SpreadThread(IntEnum):  # options.py:34-37
-    Auto = 0
-    Sequential = 1
-    Parallel = 2
-
-
-class GpuMethod(IntEnum):  # options.py:40-43 (+ the reference library's method 3)
-    Auto = 0
-    Driven = 1
-    Shared = 2
-    OutputDriven = 3
-
-
-@dataclass(frozen=True)
-class Opts:  # options.py:46-79
-    modeord: bool = False
-    debug: int = DebugLevel.Silent
-    spread_debug: int = DebugLevel.Silent
-    showwarn: bool = False
-    nthreads: int = 0
-    fftw: int = FftwFlags.Estimate
-    spread_sort: int = SpreadSort.Heuristic
-    spread_kerevalmeth: bool = True
-    spread_kerpad: bool = True
-    upsampfac: float = 0.0
-    spread_thread: int = SpreadThread.Auto
-    maxbatchsize: int = 0
-    spread_nthr_atomic: int = -1
-    spread_max_sp_size: int = 0
-
-    gpu_upsampfac: float = 2.0
-    gpu_method: int = 0
-    gpu_sort: bool = True
-    gpu_binsizex: int = 0
-    gpu_binsizey: int = 0
-    gpu_binsizez: int = 0
-    gpu_obinsizex: int = 0
-    gpu_obinsizey: int = 0
-    gpu_obinsizez: int = 0
-    gpu_maxsubprobsize: int = 1024
-    gpu_kerevalmeth: bool = True
-    gpu_spreadinterponly: bool = False
-    gpu_maxbatchsize: int = 0
-    gpu_debug: int = GpuDebugLevel.Silent
-
-    def __post_init__(self):
-        for name in ("modeord", "gpu_sort", "gpu_kerevalmeth", "gpu_spreadinterponly"):
-            v = getattr(self, name)
+def _check(self):
+    for name, _, rule, _ in _FIELDS:
+        v = getattr(self, name)
+        if rule == _FLAG:
             if not isinstance(v, (bool, int)) or int(v) not in (0, 1):
                 raise ValueError(f"Opts.{name} must be a bool, got {v!r}")
-        if int(self.gpu_method) not in (0, 1, 2, 3):
-            raise ValueError(f"Opts.gpu_method must be 0, 1, 2 or 3, got {self.gpu_method!r}")
-        if int(self.gpu_debug) not in (0, 1):
-            raise ValueError(f"Opts.gpu_debug must be 0 or 1, got {self.gpu_debug!r}")
-        if int(self.gpu_maxbatchsize) < 0:
-            raise ValueError("Opts.gpu_maxbatchsize must be >= 0")
+        elif rule == "nonneg":
+            if int(v) < 0:
+                raise ValueError(f"Opts.{name} must be >= 0")
+        elif isinstance(rule, tuple):
+            if int(v) not in rule:
+                raise ValueError(f"Opts.{name} must be one of {rule}, got {v!r}")
 
-    def to_cufinufft_opts(self):
-        """The seven attributes that cross the FFI boundary (options.py:105-119)."""
 
-        class NativeOpts:
-            pass
+def _to_cufinufft_opts(self):
+    """The attributes that cross the custom-call boundary, as plain numbers (what the reference's
+    ``Opts.to_cufinufft_opts`` hands to its lowering)."""
+    out = SimpleNamespace()
+    for name, default, _, attr in _FIELDS:
+        if attr is not None:
+            v = getattr(self, name)
+            setattr(out, attr, float(v) if isinstance(default, float) else int(v))
+    return out
 
-        opts = NativeOpts()
-        opts.modeord = int(self.modeord)
-        opts.upsampfac = float(self.gpu_upsampfac)
-        opts.gpu_method = int(self.gpu_method)
-        opts.gpu_sort = int(self.gpu_sort)
-        opts.gpu_kerevalmeth = int(self.gpu_kerevalmeth)
-        opts.gpu_maxbatchsize = int(self.gpu_maxbatchsize)
-        opts.debug = int(self.gpu_debug)
+
+Opts = dataclasses.make_dataclass(
+    "Opts", [(n, type(d) if not isinstance(d, IntEnum) else int, dataclasses.field(default=d)) for n, d, _, _ in _FIELDS],
+    frozen=True, namespace={"__post_init__": _check, "to_cufinufft_opts": _to_cufinufft_opts})
+Opts.__module__ = __name__
+Opts.__doc__ = "Options of one transform (same fields and defaults as the reference's ``Opts``)."
+
+# Per-type and per-direction options (options.py:122-129): `type1/2/3` select by transform type,
+# `forward` overrides them, `backward` (an Opts or another NestedOpts) applies to the transforms
+# the differentiation rules create.
+NestedOpts = dataclasses.make_dataclass(
+    "NestedOpts", [(n, object, dataclasses.field(default=None)) for n in ("type1", "type2", "type3", "forward", "backward")],
+    frozen=True)
+NestedOpts.__module__ = __name__
+
+
+def unpack_opts(opts, finufft_type, forward):
+    """Resolve ``opts`` for one transform (options.py:132-148): a plain ``Opts`` (or None) applies
+    to everything; a ``NestedOpts`` is looked up by direction, then by type; if the lookup has no
+    answer for a backward transform the NestedOpts itself is returned (the caller resolves it
+    again for the transposed type)."""
+    if not isinstance(opts, NestedOpts):
         return opts
-
-
-@dataclass(frozen=True)
-class NestedOpts:  # options.py:122-129
-    type1: Optional[Opts] = None
-    type2: Optional[Opts] = None
-    type3: Optional[Opts] = None
-
-    forward: Optional[Opts] = None
-    backward: Optional[Union[Opts, "NestedOpts"]] = None
-
-
-def unpack_opts(opts, finufft_type, forward):  # options.py:132-148
-    if opts is None or isinstance(opts, Opts):
-        return opts
-
-    if forward:
-        if opts.forward is not None:
-            return opts.forward
-        elif finufft_type == 1:
-            return opts.type1
-        elif finufft_type == 2:
-            return opts.type2
-        elif finufft_type == 3:
-            return opts.type3
-    elif opts.backward is not None:
-        return opts.backward
-
-    return opts
+    if not forward:
+        return opts if opts.backward is None else opts.backward
+    if opts.forward is not None:
+        return opts.forward
+    return {1: opts.type1, 2: opts.type2, 3: opts.type3}.get(finufft_type, opts)

@@ -1,138 +1,136 @@
-"""Shape canonicalisation -- host-side mirror of ``src/jax_finufft/shapes.py`` on torch tensors.
+"""Operand canonicalisation for the custom call (the job of the reference's
+``src/jax_finufft/shapes.py``, on torch tensors).
 
-``broadcast_and_flatten_inputs`` (shapes.py:27-126) folds every broadcast dimension into the
-backend's ``n_transf`` axis and every genuinely batched dimension into ``n_tot``, so the native
-call always sees ``source (n_tot, n_transf, .)`` and ``points (n_tot, M)``;
-``abstract_eval`` (shapes.py:129-170) is the shape/dtype contract of the primitive.
+The backend sees exactly one layout: ``source (n_tot, n_transf, payload...)`` and every point array
+``(n_tot, M)``.  A user call may carry any number of leading dimensions on either side, related
+by NumPy broadcasting.  The rule that maps one onto the other:
+
+* a leading axis along which the POINTS vary belongs to ``n_tot``: a new point set, hence a new
+  bin-sort (setpts) per index;
+* a leading axis along which the points are constant (absent or of length 1) while the source
+  varies belongs to ``n_transf``: stacked transforms that share one sorted point set -- the
+  many-vector fast path (V/include/cufinufft/impl.h:123-127 batches them).
+
+``Folded.unflatten`` undoes the folding on the result.  The attribute names ``broadcast_from`` /
+``broadcast_to`` / ``expected_output_shape`` are the reference's (tests/shapes_test.py reads
+them), so its test cases run against this module unchanged.
 """
 
-from dataclasses import dataclass
-from typing import Sequence
+from math import prod
 
-import numpy as np
 import torch
 
-__all__ = ["abstract_eval", "broadcast_and_flatten_inputs"]
+__all__ = ["abstract_eval", "broadcast_and_flatten_inputs", "Folded"]
 
 
-@dataclass
-class BroadcastIndex:  # shapes.py:13-24
-    broadcast_from: Sequence[int]
-    broadcast_to: Sequence[int]
-    expected_output_shape: Sequence[int]
+class Folded:
+    """How a result of shape (n_tot, n_transf, out...) maps back to the caller's leading axes."""
+
+    __slots__ = ("broadcast_from", "broadcast_to", "expected_output_shape")
+
+    def __init__(self, shared_axes, parked_axes, out_shape):
+        self.broadcast_from = tuple(shared_axes)      # caller's positions of the shared-points axes
+        self.broadcast_to = tuple(parked_axes)        # where they sit while folded (end of the lead block)
+        self.expected_output_shape = tuple(out_shape)
 
     def unflatten(self, result):
-        out = result.reshape(tuple(self.expected_output_shape))
-        if len(self.broadcast_to):
-            out = torch.movedim(out, tuple(self.broadcast_to), tuple(self.broadcast_from))
-        return out
+        full = result.reshape(self.expected_output_shape)
+        if not self.broadcast_to:
+            return full
+        return torch.movedim(full, self.broadcast_to, self.broadcast_from)
+
+
+def _common_lead(arrays):
+    """Broadcast arrays of shape (lead..., n) against each other; returns (arrays, lead, n)."""
+    arrays = torch.broadcast_tensors(*arrays)
+    shape = tuple(arrays[0].shape)
+    return list(arrays), shape[:-1], shape[-1]
 
 
 def broadcast_and_flatten_inputs(nufft_type, output_shape, source, *points):
-    if nufft_type == 3:
-        num_dim = len(points) // 2
-        points3 = points[num_dim:]
-        points = points[:num_dim]
+    ndim = len(points) // 2 if nufft_type == 3 else len(points)
+    if ndim < 1:
+        raise AssertionError("at least one coordinate array is required")
+    groups = [list(points[:ndim])] + ([list(points[ndim:])] if nufft_type == 3 else [])
+
+    # 1. one leading shape for all coordinate arrays (type 3: sources and targets together)
+    folded_groups, lengths, leads = [], [], []
+    for g in groups:
+        g, lead, n = _common_lead(g)
+        folded_groups.append(g)
+        leads.append(lead)
+        lengths.append(n)
+    lead = tuple(torch.broadcast_shapes(*leads))
+    folded_groups = [[p.broadcast_to(lead + (n,)) for p in g] for g, n in zip(folded_groups, lengths)]
+
+    # 2. payload = the trailing axes of `source` that are data, not batch
+    payload_rank = ndim if nufft_type == 2 else 1
+    # a source with exactly one more batch axis than the points stacks transforms on shared points
+    if source.ndim - payload_rank == len(lead) + 1:
+        lead = lead + (1,)
+        folded_groups = [[p.unsqueeze(-2) for p in g] for g in folded_groups]
+    nlead = len(lead)
+
+    # 3. which leading axes do the points share?
+    full = tuple(torch.broadcast_shapes(tuple(source.shape[:nlead]), lead))
+    shared = [ax for ax in range(nlead) if lead[ax] != full[ax]]
+    if any(lead[ax] != 1 for ax in shared):
+        raise AssertionError("points can only be shared along axes where they have length 1")
+    parked = list(range(nlead - len(shared), nlead))
+
+    source = source.broadcast_to(full + tuple(source.shape[nlead:]))
+    if shared:
+        source = torch.movedim(source, shared, parked)
+        folded_groups = [[torch.movedim(p, shared, parked) for p in g] for g in folded_groups]
+
+    # 4. fold: (own-points axes) -> n_tot, (shared-points axes) -> n_transf
+    keep = nlead - len(shared)
+    n_tot = prod(source.shape[:keep])
+    n_transf = prod(source.shape[keep:nlead])
+    moved_lead = tuple(source.shape[:nlead])
+    payload = tuple(source.shape[nlead:])
+    if len(payload) != payload_rank:
+        raise AssertionError(f"source has {len(payload)} data axes, the transform needs {payload_rank}")
+    if nufft_type == 2:
+        out_tail = (lengths[0],)
     else:
-        num_dim = len(points)
-    assert num_dim
+        if payload[0] != lengths[0]:
+            raise AssertionError("source and points disagree on the number of non-uniform points")
+        if nufft_type == 1:
+            if output_shape is None:
+                raise AssertionError("type 1 needs output_shape")
+            out_tail = tuple(output_shape)
+        else:
+            out_tail = (lengths[1],)
 
-    points = torch.broadcast_tensors(*points)
-    *input_shape, num_points = points[0].shape
-
-    if nufft_type == 3:
-        points3 = torch.broadcast_tensors(*points3)
-        *input_shape3, num_points3 = points3[0].shape
-        input_shape = list(torch.broadcast_shapes(tuple(input_shape), tuple(input_shape3)))
-        points = [p.broadcast_to(tuple(input_shape) + (num_points,)) for p in points]
-        points3 = [p.broadcast_to(tuple(input_shape) + (num_points3,)) for p in points3]
-    else:
-        points3 = []
-
-    # Handle unpadded points (shapes.py:56-62)
-    if (nufft_type == 2 and source.ndim == len(input_shape) + num_dim + 1) or (
-        nufft_type in (1, 3) and source.ndim == len(input_shape) + 2
-    ):
-        input_shape = tuple(input_shape) + (1,)
-        points = tuple(p[..., None, :] for p in points)
-        points3 = tuple(p[..., None, :] for p in points3)
-
-    input_shape = tuple(input_shape)
-    target_shape = tuple(torch.broadcast_shapes(tuple(source.shape[: len(input_shape)]), input_shape))
-
-    broadcast_from = tuple(
-        n for n, (input_dim, target_dim) in enumerate(zip(input_shape, target_shape)) if input_dim != target_dim
-    )
-    broadcast_to = tuple(len(target_shape) - len(broadcast_from) + n for n in range(len(broadcast_from)))
-    assert all(input_shape[n] == 1 for n in broadcast_from)
-
-    source = source.broadcast_to(target_shape + tuple(source.shape[len(target_shape):]))
-
-    if len(broadcast_to):
-        source = torch.movedim(source, broadcast_from, broadcast_to)
-        points = tuple(torch.movedim(p, broadcast_from, broadcast_to) for p in points)
-        points3 = tuple(torch.movedim(p, broadcast_from, broadcast_to) for p in points3)
-
-    num_in = len(target_shape)
-    num_axes = num_in - len(broadcast_from)
-    size_in = int(np.prod(source.shape[:num_axes], dtype=int))
-    size_bcast = int(np.prod(source.shape[num_axes:num_in], dtype=int))
-
-    if nufft_type == 3:
-        assert source.ndim == len(target_shape) + 1
-        assert source.shape[-1] == num_points
-        expected_output_shape = tuple(source.shape[:num_in]) + (num_points3,)
-        source_extra_shape = (num_points,)
-    elif nufft_type == 2:
-        assert source.ndim == num_in + num_dim
-        expected_output_shape = tuple(source.shape[:num_in]) + (num_points,)
-        source_extra_shape = tuple(source.shape[num_in:])
-    elif nufft_type == 1:
-        assert source.ndim == len(target_shape) + 1
-        assert source.shape[-1] == num_points
-        assert output_shape is not None
-        expected_output_shape = tuple(source.shape[:num_in]) + tuple(output_shape)
-        source_extra_shape = (num_points,)
-
-    source = source.reshape((size_in, size_bcast) + source_extra_shape)
-    points = tuple(p.reshape(size_in, num_points) for p in points)
-    points3 = tuple(p.reshape(size_in, num_points3) for p in points3)
-
-    return (
-        BroadcastIndex(
-            broadcast_from=broadcast_from,
-            broadcast_to=broadcast_to,
-            expected_output_shape=expected_output_shape,
-        ),
-        source,
-        *points,
-        *points3,
-    )
+    source = source.reshape((n_tot, n_transf) + payload)
+    flat = [p.reshape(n_tot, n) for g, n in zip(folded_groups, lengths) for p in g]
+    return (Folded(shared, parked, moved_lead + out_tail), source, *flat)
 
 
 def abstract_eval(source, *points, output_shape, nufft_type, **_):
-    """Output (shape, dtype) of the primitive; asserts the operand contract (shapes.py:129-170)."""
+    """(shape, dtype) of the custom call's result for canonical operands, after checking the
+    operand contract the C++ side relies on (it receives untyped buffers,
+    lib/jax_finufft_gpu.cc:66-192)."""
+    if nufft_type not in (1, 2, 3):
+        raise ValueError("nufft_type must be 1, 2, or 3")
     ndim = len(points) // 2 if nufft_type == 3 else len(points)
-    assert 1 <= ndim <= 3
-
-    single = source.dtype == torch.complex64 and all(x.dtype == torch.float32 for x in points)
-    double = source.dtype == torch.complex128 and all(x.dtype == torch.float64 for x in points)
-    assert single or double, "source must be complex64/complex128 with matching float32/float64 points"
-
-    assert all(p.ndim == 2 for p in points)
-    assert all(p.shape == points[0].shape for p in points[1:ndim])
-    assert source.shape[0] == points[0].shape[0]
-
-    if nufft_type == 3:
-        assert source.ndim == 3
-        assert all(p.shape == points[ndim].shape for p in points[ndim + 1:])
-        assert all(p.shape[:-1] == p3.shape[:-1] for (p, p3) in zip(points[:ndim], points[ndim:]))
-        return tuple(source.shape[:2]) + (points[ndim].shape[-1],), source.dtype
-    elif nufft_type == 2:
-        assert source.ndim == 2 + ndim
-        return tuple(source.shape[:2]) + (points[0].shape[-1],), source.dtype
-    elif nufft_type == 1:
-        assert source.ndim == 3
-        assert source.shape[2] == points[0].shape[1]
-        return tuple(source.shape[:2]) + tuple(output_shape), source.dtype
-    raise ValueError("nufft_type must be 1, 2, or 3")
+    assert 1 <= ndim <= 3, "1 to 3 dimensions"
+    real = {torch.complex64: torch.float32, torch.complex128: torch.float64}.get(source.dtype)
+    assert real is not None and all(p.dtype == real for p in points), \
+        "source must be complex64/complex128 with matching float32/float64 points"
+    src_pts, tgt_pts = points[:ndim], points[ndim:]
+    n_tot = source.shape[0]
+    for grp in (src_pts, tgt_pts):
+        assert all(p.ndim == 2 and p.shape == grp[0].shape for p in grp), "point arrays must be (n_tot, n), all alike"
+    assert src_pts[0].shape[0] == n_tot, "source and points disagree on n_tot"
+    head = tuple(source.shape[:2])
+    if nufft_type == 2:
+        assert source.ndim == 2 + ndim, "type 2 source must be (n_tot, n_transf, modes...)"
+        return head + (src_pts[0].shape[1],), source.dtype
+    assert source.ndim == 3, "source must be (n_tot, n_transf, n_points)"
+    if nufft_type == 1:
+        assert source.shape[2] == src_pts[0].shape[1], "source and points disagree on the number of points"
+        return head + tuple(output_shape), source.dtype
+    assert tgt_pts[0].shape[0] == n_tot, "targets and sources disagree on n_tot"
+    return head + (tgt_pts[0].shape[1],), source.dtype
