@@ -12,7 +12,12 @@ points and the clustered distribution are measured too and reported under ``also
 
 N>1 (torchrun): the path shards over independent transforms (n_tot / vmapped batch): every
 rank runs its own M=1e8 transform on its own GPU, no data-path collective -> weak scaling;
-``value`` = N*M / max-over-ranks time.
+``value`` = N*M / max-over-ranks time.  The sharded configs BASELINE.json names are timed in the
+same run and reported under ``also``: ``c4_stacked`` (config 4: 64 stacked 2-D type-1 transforms
+sharing M=1e7 points, N=1024^2, the stack split across the ranks -- strong scaling, the N=1 run is
+its own baseline) and ``c3_t1_points_sharded`` (ONE 3-D type 1 with its points split by range).
+``also.ref_gpu`` times the unmodified reference cuFINUFFT (oracle/_ref, when it travelled to the
+box) on the same tensors with the protocol of V/perftest/cuda/cuperftest.cu:183-303.
 """
 import argparse
 import ctypes as C
@@ -37,6 +42,7 @@ WORKLOADS = {
     "c3_t2_clustered": (2, 10 ** 8, (256, 256, 256), 1e-6, "clustered"),
     "small_t1": (1, 10 ** 6, (64, 64, 64), 1e-6, "uniform"),   # dev only
 }
+C4 = dict(n_transf=64, M=10 ** 7, nm=(1024, 1024), eps=1e-6)   # BASELINE.json configs[3]
 METRIC = "NU points/sec, 3-D type-{t} (eps=1e-6, complex64, M=1e8, N=256^3), setpts+execute per step"
 UNIT = "NU points/s"
 
@@ -49,8 +55,30 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3_t1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true", help="skip also/e2e/cpu_baseline legs (profiling runs)")
-    ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="points per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000, help="points of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-full", dest="cpu_full", action="store_false",
+                    help="--impl reference: time --cpu-sample points per step instead of the full M (CPU-only smoke runs)")
     return ap.parse_args()
+
+
+def make_config(workload, world):
+    """The workload description both arms print (same keys, same values)."""
+    typ, M, nm, eps, dist = WORKLOADS[workload]
+    return {"workload": workload, "type": typ, "M_per_gpu": M, "N": list(nm), "eps": eps, "points": dist,
+            "seed": "1+rank", "n_gpus": world}
+
+
+def src_sha16():
+    """Hash of the library's sources (csrc/ + include/): stamps which code an ncu capture measured."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(ROOT, "jax_finufft_b200", "csrc", "*.*")) + glob.glob(os.path.join(ROOT, "include", "*.h")))
+    for f in files:
+        if os.path.isfile(f):
+            h.update(os.path.basename(f).encode())
+            h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
 # ----------------------------------------------------------------------------- synthetic inputs
@@ -118,46 +146,58 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_port_rate(typ, M_full, nm, eps, sample, steps, warmup):
-    """Times oracle/nufft_oracle.c (OpenMP, all host threads) on a bounded sample: the full
-    N=256^3 pipeline on `sample` points per step and, for the M-independent cost (FFT +
-    deconvolve), on sample/10 points -- both warm, same code path; the per-point cost is the slope
-    between the two, extrapolated linearly in M to the full workload."""
+def _oracle_threads():
     import oracle
 
     try:  # all the host cores this process may use, whatever OMP_NUM_THREADS the launcher exported
         oracle.set_num_threads(len(os.sched_getaffinity(0)))
     except AttributeError:
         oracle.set_num_threads(os.cpu_count() or 1)
-    rng = np.random.default_rng(1)
-    x = rng.uniform(-np.pi, np.pi, size=(3, sample))
+    return oracle
+
+
+def _cpu_runner(typ, nm, eps, M, seed=1):
+    """-> run(n): the full N=256^3 oracle pipeline on the first n of M seeded points."""
+    oracle = _oracle_threads()
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-np.pi, np.pi, size=(3, M))
     nmx = tuple(nm[::-1])
     if typ == 1:
-        d = rng.uniform(-1, 1, sample) + 1j * rng.uniform(-1, 1, sample)
-        run = lambda n: oracle.nufft1(nmx, d[:n], *x[:, :n], eps=eps, prec=1)
-    else:
-        d = rng.uniform(-1, 1, nm) + 1j * rng.uniform(-1, 1, nm)
-        run = lambda n: oracle.nufft2(d, *x[:, :n], eps=eps, prec=1)
+        d = rng.uniform(-1, 1, M) + 1j * rng.uniform(-1, 1, M)
+        return lambda n: oracle.nufft1(nmx, d[:n], *x[:, :n], eps=eps, prec=1)
+    d = rng.uniform(-1, 1, nm) + 1j * rng.uniform(-1, 1, nm)
+    return lambda n: oracle.nufft2(d, *x[:, :n], eps=eps, prec=1)
 
-    def clock(n):
-        t0 = time.perf_counter(); run(n); return time.perf_counter() - t0
 
+def _clock(run, n):
+    t0 = time.perf_counter()
+    run(n)
+    return time.perf_counter() - t0
+
+
+def cpu_port_sample(typ, M_full, nm, eps, sample):
+    """cpu_baseline of the GPU arm: oracle/nufft_oracle.c (OpenMP, all host threads) on a BOUNDED
+    sample -- the full N=256^3 pipeline on `sample` points and, for the M-independent cost (FFT +
+    deconvolve), on sample/10 points, both warm; the per-point cost is the slope between the two,
+    extrapolated linearly in M (flagged).  The reference arm (--impl reference) runs the full M."""
+    import oracle
+
+    run = _cpu_runner(typ, nm, eps, sample)
     small = max(1000, sample // 10)
-    clock(small)                                  # first touch of the grids, thread pool, FFT tables
-    t_small = min(clock(small), clock(small))
-    for _ in range(max(0, warmup - 1)):
-        run(sample)
-    t_step = statistics.mean(clock(sample) for _ in range(steps))
+    _clock(run, small)                            # first touch of the grids, thread pool, FFT tables
+    t_small = min(_clock(run, small), _clock(run, small))
+    _clock(run, sample)
+    t_step = _clock(run, sample)
     per_pt = max(t_step - t_small, 0.0) / (sample - small)
     t_fixed = max(t_small - per_pt * small, 0.0)
     t_full = t_fixed + per_pt * M_full
     return {
-        "value": M_full / t_full, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-        "sample": (f"oracle/nufft_oracle.c (float64 restatement, OpenMP x{oracle.num_threads()}): {steps} steps of the full "
-                   f"N=256^3 pipeline on {sample} points ({t_step:.2f} s/step; {t_small:.2f} s on {small} points => "
-                   f"{per_pt * 1e9:.0f} ns/point + {t_fixed:.2f} s M-independent FFT/deconvolve), extrapolated linearly "
-                   f"in M to M={M_full}: {t_full:.1f} s; the reference CPU FINUFFT (xsimd+FFTW) cannot be built offline "
-                   "(SURVEY.md §8c)"),
+        "value": M_full / t_full, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "extrapolated": True,
+        "sample": (f"oracle/nufft_oracle.c (float64 restatement, OpenMP x{oracle.num_threads()}): the full N=256^3 pipeline on "
+                   f"{sample} points ({t_step:.2f} s; {t_small:.2f} s on {small} points => {per_pt * 1e9:.0f} ns/point + "
+                   f"{t_fixed:.2f} s M-independent FFT/deconvolve), extrapolated linearly in M to M={M_full}: {t_full:.1f} s. "
+                   "`bench.py --impl reference` times the full M.  The reference CPU FINUFFT (xsimd+FFTW) cannot be built "
+                   "offline (SURVEY.md 8c)"),
         "ms_per_step_extrapolated": t_full * 1e3,
     }
 
@@ -183,22 +223,84 @@ def _emit(line):
 
 
 def main_reference(a):
+    """Reference arm: the CPU implementation of the path on the host cores (the oracle port; the
+    reference's own FINUFFT cannot be built offline), all host threads, on the FULL workload --
+    M points per step, nothing extrapolated.  A step costs tens of seconds, so steps/warm-up are
+    capped (the line states what ran) to keep the run within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import oracle
+
     typ, M, nm, eps, dist = WORKLOADS[a.workload]
-    steps = max(1, min(a.steps, 5))
-    cb = cpu_port_rate(typ, M, nm, eps, a.cpu_sample, steps, min(a.warmup, 1))
+    steps = max(1, min(a.steps, 2 if a.cpu_full else 3))
+    warm = 1
+    M_run = M if a.cpu_full else min(M, a.cpu_sample)
+    run = _cpu_runner(typ, nm, eps, M_run)
+    for _ in range(warm):
+        _clock(run, M_run if not a.cpu_full else max(1000, M_run // 10))   # tables, thread pool, first touch
+    ts = [_clock(run, M_run) for _ in range(steps)]
+    t_step = statistics.mean(ts)
+    cfg = make_config(a.workload, a.gpus)
+    cb = {"value": M_run / t_step, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "extrapolated": False,
+          "sample": (f"oracle/nufft_oracle.c (float64 restatement, OpenMP x{oracle.num_threads()}): {steps} timed steps of the full "
+                     f"N=256^3 pipeline on M={M_run} points, {t_step:.2f} s/step (warm-up: one pass on "
+                     f"{M_run if not a.cpu_full else max(1000, M_run // 10)} points); the reference CPU FINUFFT (xsimd+FFTW) cannot "
+                     "be built offline (SURVEY.md 8c)")}
+    if M_run != M:
+        cfg["M_per_gpu"] = M_run
+        cb["sample"] += f"; --no-cpu-full: bounded to {M_run} of {M} points"
     line = {
         "impl": "reference", "metric": METRIC.format(t=typ), "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
-        "steps": steps, "warmup": min(a.warmup, 1), "ms_per_step": cb["ms_per_step_extrapolated"],
+        "steps": steps, "warmup": warm, "ms_per_step": t_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": a.workload, "type": typ, "M": M, "N": list(nm), "eps": eps, "points": dist},
-        "cpu_baseline": cb,
+        "config": cfg, "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _emit(line)
+
+
+# ----------------------------------------------------------------------------- reference GPU kernels
+def ref_gpu_leg(workload, timed):
+    import torch
+    try:
+        from oracle import ref_cufinufft as ref
+    except Exception as ex:  # noqa: BLE001
+        return {"unavailable": f"oracle.ref_cufinufft: {ex}"}
+    if not ref.available():
+        return {"unavailable": "oracle/_ref/libcufinufft_ref.so not present (built by oracle/Makefile.ref where /root/reference exists)"}
+    res = {"library": "oracle/_ref/libcufinufft_ref.so = vendor/finufft @ the reference's pin, unmodified, sm_100",
+           "protocol": "V/perftest/cuda/cuperftest.cu:183-303"}
+    for name in ("c3_t1", "c3_t2"):
+        try:
+            typ, M, nm, eps, distn, pts, data, step = workload(name)
+            isign = 1 if typ == 1 else -1
+            out = torch.empty((1,) + tuple(nm) if typ == 1 else (1, M), dtype=torch.complex64, device=data.device)
+
+            def per_call():
+                r = ref.RefPlan(typ, nm[::-1], n_trans=1, eps=eps, isign=isign)
+                r.setpts(pts[2], pts[1], pts[0])
+                r.execute(data[None], out=out)
+                r.destroy()
+
+            r = ref.RefPlan(typ, nm[::-1], n_trans=1, eps=eps, isign=isign)
+
+            def kept():
+                r.setpts(pts[2], pts[1], pts[0])
+                r.execute(data[None], out=out)
+
+            ms_kept, _ = timed(kept, 3, 1)
+            r.destroy()
+            ms_call, _ = timed(per_call, 3, 1)
+            ms_ours, _ = timed(step, 3, 2)
+            res[name] = {"ref_ms_plan_kept": ms_kept, "ref_ms_plan_per_call": ms_call, "ours_ms": ms_ours,
+                         "speedup_plan_kept": ms_kept / ms_ours, "speedup_plan_per_call": ms_call / ms_ours}
+            del pts, data, step, out
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            res[name] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+    return res
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -274,10 +376,10 @@ def main_ours(a):
         "metric": METRIC.format(t=typ), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": a.workload, "type": typ, "M_per_gpu": M, "N": list(nm), "eps": eps, "points": distn,
-                   "seed": "1+rank", "step": "b2n_run = setpts (bin-sort) + execute, plan cached",
-                   "l2": "inputs (2.0 GB points+strengths, 1.07 GB fine grid) exceed the 126 MB L2; no explicit flush",
-                   "sharding": "independent transforms per GPU (n_tot split), no data-path collective" if world > 1 else "single GPU"},
+        "config": make_config(a.workload, world),
+        "notes": {"step": "b2n_run = setpts (bin-sort) + execute, plan cached",
+                  "l2": "inputs (2.0 GB points+strengths, 1.07 GB fine grid) exceed the 126 MB L2; no explicit flush",
+                  "sharding": "independent transforms per GPU (n_tot split), no data-path collective" if world > 1 else "single GPU"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
 
@@ -301,13 +403,21 @@ def main_ours(a):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
             peak = float(peaks.get("hbm_gbs", 6650.0))
             achieved = alg_bytes / (st[kern] * 1e-3) / 1e9
-            traffic = None
+            # measured DRAM bytes of that kernel: one `ncu --set full` capture per change
+            # (tools/gpu_round.sh -> tools/traffic_stamp.py), stamped with the hash of the sources it
+            # was taken on; a capture of other sources is reported but flagged
+            traffic, capture = None, None
             tf = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tf):
-                traffic = json.load(open(tf)).get(f"{a.workload}:{kern}")
-            line["roofline"] = {"bound": "hbm", "kernel": "k_swr_spread<7>" if typ == 1 else "k_swr_interp<7>",
+                ent = json.load(open(tf)).get(f"{a.workload}:{kern}")
+                if isinstance(ent, dict):
+                    traffic = ent.get("bytes")
+                    capture = {"tag": ent.get("tag"), "kernel": ent.get("kernel"), "src_sha16": ent.get("src_sha16"),
+                               "same_sources_as_this_run": ent.get("src_sha16") == src_sha16()}
+            line["roofline"] = {"bound": "hbm", "kernel": "k_swr2_spread<7>" if typ == 1 else "k_swr2_interp<7>",
                                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                "traffic": traffic, "algorithmic_bytes": alg_bytes, "kernel_ms": st[kern],
+                                "traffic": traffic, "traffic_capture": capture,
+                                "algorithmic_bytes": alg_bytes, "kernel_ms": st[kern],
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                                 "note": "3-D ns=7 spread/interp is FP32-pipe/issue-bound (343 complex cell updates per point, kept in "
                                         "registers), see DESIGN.md 4.2; HBM fraction reported as the contract asks",
@@ -382,6 +492,37 @@ def main_ours(a):
             L.b2n_cache_clear()
         line["also"] = also
 
+        # ---- BASELINE config 4: 64 stacked 2-D type-1 transforms sharing M=1e7 points, N=1024^2, the
+        # stack split across the ranks (points replicated, every rank repeats the bin-sort, no
+        # collective: ref README.md:364-367).  STRONG scaling: total work fixed, the N=1 run is the
+        # baseline the driver's 1/2/4/8 sweep divides by.
+        if a.workload == "c3_t1":
+            from jax_finufft_b200 import parallel as P
+            try:
+                g4 = torch.Generator(device=dev).manual_seed(3)   # same points and strengths on every rank
+                p4 = [(torch.rand(C4["M"], device=dev, generator=g4) * 2 - 1) * np.pi for _ in range(2)]
+                c4 = make_complex((C4["n_transf"], C4["M"]), dev, g4)
+                fn = lambda: P.nufft1_stacked(C4["nm"], c4, *p4, gather=False, eps=C4["eps"], iflag=1)
+                ms4, _ = timed(fn, 5, 3)
+                nloc = len(range(*P.shard_range(C4["n_transf"], world, rank)))
+                also["c4_stacked"] = {"value": C4["n_transf"] * C4["M"] / (ms4 * 1e-3), "unit": "NU point-transforms/s",
+                                      "ms_per_step": ms4, "steps": 5, "scaling": "strong", "n_transf": C4["n_transf"],
+                                      "n_transf_per_gpu": nloc, "M": C4["M"], "N": list(C4["nm"]), "eps": C4["eps"],
+                                      "step": "setpts (bin-sort, repeated per rank) + execute of this rank's share of the stack"}
+                del p4, c4, fn
+            except Exception as ex:  # noqa: BLE001  (auxiliary leg: must not cost the headline line)
+                also["c4_stacked"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+            torch.cuda.empty_cache()
+            L.b2n_cache_clear()
+
+        # ---- the kernel to beat: the UNMODIFIED reference cuFINUFFT (oracle/_ref, built from
+        # /root/reference by oracle/Makefile.ref) on the same B200 and the same tensors, timed the way
+        # V/perftest/cuda/cuperftest.cu:183-303 does (CUDA events; setpts + execute with the plan kept)
+        # and the way jax-finufft drives it (makeplan + setpts + execute + destroy per call,
+        # lib/kernels.cc.cu:49-92).  Checker/baseline only: nothing of it is on our path.
+        if rank == 0 and world == 1 and a.workload.startswith("c3"):
+            also["ref_gpu"] = ref_gpu_leg(workload, timed)
+
         # ---- N > 1: the one path with a real exchange step: ONE 3-D type 1 with its
         # M points split across the ranks by index range (strong scaling of a single transform).
         # slab = spatial split (points exchanged by z-slab, spread into slab + halo, halo planes to the
@@ -423,7 +564,7 @@ def main_ours(a):
 
         # ---- CPU baseline: the oracle port on the host cores (rank 0, N=1 only)
         if rank == 0 and world == 1:
-            line["cpu_baseline"] = cpu_port_rate(typ, M, nm, eps, a.cpu_sample, 2, 1)
+            line["cpu_baseline"] = cpu_port_sample(typ, M, nm, eps, a.cpu_sample)
 
     if rank == 0:
         _emit(line)

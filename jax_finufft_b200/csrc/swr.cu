@@ -1,5 +1,12 @@
 // swr.cu -- ns dispatch + launch of the sliding-window register kernels (3-D, float, ns <= 8).
 #include "rt2_kernels.cuh"
+#include "swr2_kernels.cuh"
+
+// generation of the 3-D sliding-window kernels: 2 = swr2_kernels.cuh (absolute ring slots), 1 = the
+// phase-chain kernels of swr_kernels.cuh (kept for A/B builds: make EXTRA=-DSWR_GEN=1)
+#ifndef SWR_GEN
+#define SWR_GEN 2
+#endif
 
 namespace b2n {
 
@@ -42,10 +49,17 @@ static void swr_fill(Plan<float> &p, SwrArgs &a) {
 template <int NS> struct SwrDispatch {
   static int spread(Plan<float> &p, const SwrArgs &a, int ntr) {
     if (p.ns == NS) {
+#if SWR_GEN == 2
+      using C = Swr2Cfg<NS>;
+      dim3 grid((unsigned)p.pts.sp_cap, (unsigned)ntr);
+      B2N_CUDA_OK(cudaFuncSetAttribute(k_swr2_spread<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SPREAD_SMEM));
+      k_swr2_spread<NS><<<grid, 32, C::SPREAD_SMEM, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
+#else
       using C = SwrCfg<NS>;
       dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
       B2N_CUDA_OK(cudaFuncSetAttribute(k_swr_spread<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes()));
       k_swr_spread<NS><<<grid, 32 * C::WARPS, C::smem_bytes(), p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
+#endif
       B2N_LAUNCH_OK();
       return 0;
     }
@@ -53,11 +67,18 @@ template <int NS> struct SwrDispatch {
   }
   static int interp(Plan<float> &p, const SwrArgs &a, int ntr) {
     if (p.ns == NS) {
+#if SWR_GEN == 2
+      using C = Swr2Cfg<NS>;
+      dim3 grid((unsigned)p.pts.sp_cap, (unsigned)ntr);
+      B2N_CUDA_OK(cudaFuncSetAttribute(k_swr2_interp<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::INTERP_SMEM));
+      k_swr2_interp<NS><<<grid, 32, C::INTERP_SMEM, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
+#else
       using C = SwrCfg<NS>;
       const size_t smem = SwrInterpSmem<NS>::bytes();
       B2N_CUDA_OK(cudaFuncSetAttribute(k_swr_interp<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
       k_swr_interp<NS><<<grid, 32 * C::WARPS, smem, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
+#endif
       B2N_LAUNCH_OK();
       return 0;
     }

@@ -1,0 +1,715 @@
+// swr2_kernels.cuh -- second generation of the sliding-window REGISTER kernels (3-D, float, ns <= 8).
+// Same decomposition as swr_kernels.cuh (one warp per subproblem, 8 x 12 cell window, a ring of
+// D = ns z planes in registers, points in anchor-z order), different control structure:
+//
+//   * ABSOLUTE RING SLOTS.  Plane p (counted from a per-subproblem base zb) lives in ring slot
+//     p mod D for the whole subproblem.  The lane that evaluates a point's kernel vectors stores
+//     the z weights already rotated into slot order (slot (p0 + j) mod D holds kz[j]), so the
+//     FMA block is ONE straight-line piece of code -- acc[s][k] += wv[s] * kzslot[k], k literal --
+//     for every point, whatever plane its window starts at.  The first generation reached literal
+//     accumulator indices by instantiating the whole loop body D times (a chain of phases entered
+//     through a switch): 7x the code (instruction-cache misses, `no_instruction` stalls) and ~9
+//     control instructions per point to move between phases.
+//   * SENTINEL-TERMINATED RUNS.  Row nb of a batch carries META = -1, every real row
+//     META = ((plane << 1 | half) << 2 | y class) >= 0, so the inner loop is
+//     `while (meta == key) { point; }` -- one compare and one branch per point, no point counter,
+//     no end-of-batch test.  Plane changes (retire / fetch a plane), half-batch boundaries
+//     (interpolation: reduce the partial results) and the end of the batch all surface as a key
+//     change and are handled outside the loop.
+//   * the row piece that carries META is rolled first, so the loop branch never waits on a load.
+//   * Interpolation stages the NEXT planes of the window through shared memory with cp.async
+//     (LDGSTS, 8 bytes per lane and row slot, SWR2_STG planes ahead, one commit group per plane):
+//     the first generation kept one plane of look-ahead in registers and stalled on it
+//     (long-scoreboard ~1 per issue: a plane is consumed every ~2800 cycles, less than the latency
+//     of a fine-grid line under the random 32-byte output scatter the same kernel produces).
+//     Bulk/TMA copies (cp.async.bulk / cp.async.bulk.tensor) need 16-byte aligned rows; a window
+//     row starts at an odd cell (x0 - ns/2, 8-byte aligned) and wraps periodically, so the
+//     per-lane LDGSTS form is the one that fits.  SWR2_STAGE=0 rebuilds the register look-ahead
+//     with an L2 prefetch SWR2_PF planes ahead.
+#pragma once
+#include "swr_kernels.cuh"
+
+namespace b2n {
+
+#ifndef SWR2_STAGE
+#define SWR2_STAGE 1
+#endif
+#ifndef SWR2_STG
+#define SWR2_STG 4  // planes in flight (cp.async ring)
+#endif
+#ifndef SWR2_PF
+#define SWR2_PF 3   // L2 prefetch distance of the register look-ahead variant
+#endif
+#ifndef SWR2_YCLASS_INTERP
+#define SWR2_YCLASS_INTERP 1
+#endif
+
+constexpr int SWR2_SENTINEL = -1;
+
+// Row of one point in shared memory (floats).  Differences from SwrCfg: META sits in the unused
+// fourth column of the y block (one copy per lane row, so it arrives with the y weights, first
+// thing in the FMA block), and the z block holds only the D weights, in RING-SLOT order.
+template <int NS> struct Swr2Cfg : SwrCfg<NS> {
+  using B = SwrCfg<NS>;
+  static constexpr int KXO = 0;                 // WX pairs: spread (c.re*kx, c.im*kx); interp (kx, kx)
+  static constexpr int KYO = 2 * B::WX;         // [r = row & 3]{ky(r), ky(4 + r), ky(8 + r), META}
+  static constexpr int KZO = KYO + 16;          // D z weights by ring slot
+  static constexpr int KZW = (B::D + 3) & ~3;
+  static constexpr int ROW0 = KZO + KZW;
+  static constexpr int ROW = (ROW0 / 4) % 2 == 1 ? ROW0 : ROW0 + 4;  // stride/4 odd (see SwrCfg)
+  static constexpr int NV = KZW / 4;
+  static constexpr int NROWS = B::PB + 1;       // + the sentinel row of a full batch
+  static constexpr int ZBIAS = 16 * B::D;       // planes are counted from zb = z0 - H - ZBIAS: always > 0
+  static constexpr int SPREAD_FLOATS = NROWS * ROW;
+  static constexpr int SPREAD_SMEM = SPREAD_FLOATS * (int)sizeof(float);
+  // interp: rows + RES[16][33] float2 + the staging ring [STG][S][32] of float2 (x CX)
+  static constexpr int RES_OFF = SPREAD_FLOATS;
+  static constexpr int STG_OFF = RES_OFF + 2 * 16 * 33;  // 1056 floats: stays 16-byte aligned
+  static constexpr int INTERP_FLOATS = STG_OFF + (SWR2_STAGE ? SWR2_STG * B::S * 32 * 2 * B::CX : 0);
+  static constexpr int INTERP_SMEM = INTERP_FLOATS * (int)sizeof(float);
+  static_assert(B::S <= 3, "META uses the fourth y column");
+};
+
+__device__ __forceinline__ bool swr2_decode(const SwrArgs &a, int sp, int &first, int &cnt, int &x0, int &y0, int &z0) {
+  if (sp >= a.sp_off[a.nbins]) return false;
+  const int b = a.sp_bin[sp];
+  const int s = sp - a.sp_off[b];
+  first = a.bin_start[b] + s * a.maxsub;
+  cnt = min(a.maxsub, a.bin_start[b + 1] - first);
+  const int bxy = a.nbin[0] * a.nbin[1];
+  const int bz = b / bxy, r = b - bz * bxy;
+  const int by = r / a.nbin[0];
+  x0 = (r - by * a.nbin[0]) * a.bin[0];
+  y0 = by * a.bin[1];
+  z0 = bz * a.bin[2];
+  return cnt > 0;
+}
+
+// shared-memory accesses by 32-bit shared address: no generic-to-shared conversion in the loops
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(unsigned a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+
+// the three kernel vectors of one point in one Horner sweep, two intervals per FFMA2; NC > 0:
+// coefficient count known at compile time (fully unrolled, no loop bookkeeping)
+template <int NS, int NC>
+__device__ __forceinline__ void swr2_horner(const HornerTable<float> &tab, float zx, float zy, float zz,
+                                            float (&kx)[2 * SwrCfg<NS>::NP], float (&ky)[2 * SwrCfg<NS>::NP],
+                                            float (&kz)[2 * SwrCfg<NS>::NP]) {
+  constexpr int NP = SwrCfg<NS>::NP;
+  const float2 zx2 = make_float2(zx, zx), zy2 = make_float2(zy, zy), zz2 = make_float2(zz, zz);
+  float2 ax[NP], ay[NP], az[NP];
+#pragma unroll
+  for (int j = 0; j < NP; j++) ax[j] = ay[j] = az[j] = make_float2(tab.c[0][2 * j], tab.c[0][2 * j + 1]);
+  auto step = [&](int k) {
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+      const float2 cj = make_float2(tab.c[k][2 * j], tab.c[k][2 * j + 1]);
+      ax[j] = fma2(ax[j], zx2, cj);
+      ay[j] = fma2(ay[j], zy2, cj);
+      az[j] = fma2(az[j], zz2, cj);
+    }
+  };
+  if constexpr (NC > 0) {
+#pragma unroll
+    for (int k = 1; k < NC; k++) step(k);
+  } else {
+    for (int k = 1; k < tab.ncoef; k++) step(k);
+  }
+#pragma unroll
+  for (int j = 0; j < NP; j++) {
+    kx[2 * j] = ax[j].x; kx[2 * j + 1] = ax[j].y;
+    ky[2 * j] = ay[j].x; ky[2 * j + 1] = ay[j].y;
+    kz[2 * j] = az[j].x; kz[2 * j + 1] = az[j].y;
+  }
+}
+
+// lane t parks the weights of its point in `row` (layout: Swr2Cfg).  The z weights go to their
+// ring slots: plane prel + j (prel = first plane of the window, counted from the subproblem's
+// base) -> row[KZO + (prel + j) mod D].  meta = ((prel << 1 | half) << 2) | cls.
+template <int NS>
+__device__ __forceinline__ void swr2_weights(const HornerTable<float> &tab, const float4 pr4, float2 cv, int xa,
+                                             int ya, int zb, float *row, int half, int cls) {
+  using C = Swr2Cfg<NS>;
+  constexpr int NP = C::NP, D = C::D;
+  const float px = pr4.x, py = pr4.y, pz = pr4.z;
+  const int isx = window_start(px, NS), isy = window_start(py, NS), isz = window_start(pz, NS);
+  const int prel = isz - zb;  // > 0 (ZBIAS)
+  {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 m4 = make_float4(0.f, 0.f, 0.f, __int_as_float((((prel << 1) | half) << 2) | cls));
+#pragma unroll
+    for (int i = 0; i < C::KYO / 4; i++) reinterpret_cast<float4 *>(row)[i] = z4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) reinterpret_cast<float4 *>(row + C::KYO)[i] = m4;
+  }
+  float kx[2 * NP], ky[2 * NP], kz[2 * NP];
+  if (!tab.direct) {
+    const float zx = fmaf(2.f, float(isx) - px, float(NS - 1));
+    const float zy = fmaf(2.f, float(isy) - py, float(NS - 1));
+    const float zz = fmaf(2.f, float(isz) - pz, float(NS - 1));
+    // coefficient count horner_fit (hostmath.cpp) settles on for float tables at sigma = 2; any
+    // other table (sigma = 1.25, ...) takes the run-time loop
+    constexpr int NC = NS == 2 ? 6 : NS == 3 ? 5 : NS == 4 ? 8 : NS == 5 ? 7 : 9;
+    if (tab.ncoef == NC) swr2_horner<NS, NC>(tab, zx, zy, zz, kx, ky, kz);
+    else swr2_horner<NS, 0>(tab, zx, zy, zz, kx, ky, kz);
+  } else {
+    float tx[NS], ty[NS], tz[NS];
+    eval_kernel<float, NS>(tx, float(isx) - px, tab);
+    eval_kernel<float, NS>(ty, float(isy) - py, tab);
+    eval_kernel<float, NS>(tz, float(isz) - pz, tab);
+#pragma unroll
+    for (int j = 0; j < NS; j++) { kx[j] = tx[j]; ky[j] = ty[j]; kz[j] = tz[j]; }
+  }
+  {
+    int xl = isx - xa;
+    xl = xl < 0 ? 0 : (xl > C::WX - NS ? C::WX - NS : xl);
+    float2 *dst = reinterpret_cast<float2 *>(row + C::KXO) + xl;
+#pragma unroll
+    for (int j = 0; j < NS; j++) dst[j] = mul2(cv, make_float2(kx[j], kx[j]));
+  }
+  {
+    int yl = isy - ya;
+    yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+      const int iy = yl + j;
+      row[C::KYO + 4 * (iy & 3) + (iy >> 2)] = ky[j];
+    }
+  }
+  {
+    const unsigned sl = (unsigned)prel % (unsigned)D;
+    float *kzr = row + C::KZO;
+#pragma unroll
+    for (int j = 0; j < NS; j++) kzr[min(sl + j, sl + j - D)] = kz[j];  // (sl + j) mod D: the wrapped term underflows
+  }
+}
+
+// One point's row as the inner loops hold it: this lane's x weight(s), its y weights + META, the
+// D (kz, kz) scalars by ring slot.  The loops keep ONE such set live and reload each piece from
+// the NEXT row right after its last use ("rolling" loads).
+template <int NS> struct Swr2Row {
+  using C = Swr2Cfg<NS>;
+  static constexpr int NV = C::NV;
+  float4 kv[NV];
+  float2 cx[C::CX];
+  float4 ky;  // .w = META
+  __device__ __forceinline__ void load_xy(unsigned ax, unsigned ay) {
+    if constexpr (C::CX == 1) {
+      cx[0] = lds64(ax);
+    } else {
+      const float4 v = lds128(ax);
+      cx[0] = make_float2(v.x, v.y);
+      cx[1] = make_float2(v.z, v.w);
+    }
+    ky = lds128(ay);
+  }
+  __device__ __forceinline__ void load_kv(unsigned az, int i) { kv[i] = lds128(az + 16 * i); }
+  __device__ __forceinline__ void load_all(unsigned ax, unsigned ay, unsigned az) {
+    load_xy(ax, ay);
+#pragma unroll
+    for (int i = 0; i < NV; i++) load_kv(az, i);
+  }
+  __device__ __forceinline__ float2 kz(int j) const {  // (kz, kz): a scalar-broadcast FFMA2 operand
+    const float4 v = kv[j / 4];
+    const float k = (j & 3) == 0 ? v.x : ((j & 3) == 1 ? v.y : ((j & 3) == 2 ? v.z : v.w));
+    return make_float2(k, k);
+  }
+  __device__ __forceinline__ int meta() const { return __float_as_int(ky.w); }
+  __device__ __forceinline__ float2 kyv(int s) const {
+    const float k = s == 0 ? ky.x : (s == 1 ? ky.y : ky.z);
+    return make_float2(k, k);
+  }
+};
+
+// ==================================================================================== SPREAD
+template <int NS>
+__global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
+    k_swr2_spread(const SwrArgs a, const __grid_constant__ HornerTable<float> tab) {
+  using C = Swr2Cfg<NS>;
+  constexpr int D = C::D, S = C::S, CX = C::CX, NV = C::NV;
+  extern __shared__ __align__(16) float swr_smem[];
+  const int lane = threadIdx.x;
+  int first, cnt, x0, y0, z0;
+  if (!swr2_decode(a, blockIdx.x, first, cnt, x0, y0, z0)) return;
+  float *rows = swr_smem;
+  const float2 *cin = a.cin + (int64_t)blockIdx.y * a.M;
+
+  const int r = lane >> 3, q = lane & 7;
+  const int xa = x0 - C::H, ya = y0 - C::H, zb = z0 - C::H - C::ZBIAS;
+  const int nf0 = a.nf[0], nf1 = a.nf[1], nf2 = a.nf[2];
+  const int64_t pstride = (int64_t)nf0 * nf1;
+  float2 *cell[S];  // this lane's cell of each row slot in plane 0
+#pragma unroll
+  for (int s = 0; s < S; s++)
+    cell[s] = a.fw + (int64_t)blockIdx.y * a.nftot +
+              (wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0));
+
+  float2 acc[S][CX][D];
+#pragma unroll
+  for (int s = 0; s < S; s++)
+#pragma unroll
+    for (int c = 0; c < CX; c++)
+#pragma unroll
+      for (int k = 0; k < D; k++) acc[s][c][k] = make_float2(0.f, 0.f);
+
+  // retire relative plane prel held by ring slot `slot`: RED this lane's cells, clear the slot
+  auto retire = [&](int slot, int prel) {
+    int gz = prel + zb;
+    gz = gz < 0 ? gz + nf2 : gz;
+    if (gz >= nf2) gz = gz - nf2 < nf2 ? gz - nf2 : gz % nf2;
+    const int64_t po = (int64_t)gz * pstride;
+    auto one = [&](auto kc) {
+      constexpr int K = decltype(kc)::value;
+      if constexpr (K < D) {
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+          if constexpr (CX == 1) {
+            red_add(cell[s] + po, acc[s][0][K]);
+          } else {
+            red_add4(reinterpret_cast<float4 *>(cell[s] + po),
+                     make_float4(acc[s][0][K].x, acc[s][0][K].y, acc[s][1][K].x, acc[s][1][K].y));
+          }
+#pragma unroll
+          for (int c = 0; c < CX; c++) acc[s][c][K] = make_float2(0.f, 0.f);
+        }
+      }
+    };
+    switch (slot) {
+      case 0: one(std::integral_constant<int, 0>{}); break;
+      case 1: one(std::integral_constant<int, 1>{}); break;
+      case 2: one(std::integral_constant<int, 2>{}); break;
+      case 3: one(std::integral_constant<int, 3>{}); break;
+      case 4: one(std::integral_constant<int, 4>{}); break;
+      case 5: one(std::integral_constant<int, 5>{}); break;
+      case 6: one(std::integral_constant<int, 6>{}); break;
+      default: one(std::integral_constant<int, 7>{}); break;
+    }
+  };
+
+  Swr2Row<NS> pr;
+  // this lane's pieces of the row being consumed (32-bit shared addresses; + ROW per point)
+  const unsigned ax0 = smem_u32(rows + C::KXO + 2 * CX * q), ay0 = smem_u32(rows + C::KYO + 4 * r),
+                 az0 = smem_u32(rows + C::KZO);
+  unsigned ax = ax0, ay = ay0, az = az0;
+  constexpr unsigned RB = C::ROW * sizeof(float);
+  // all ns^2 x ns cell updates of the point held in `pr`, then roll `pr` on to the next row.
+  // CLS: 0 = the point's y window ends below row slot S-1, 2 = it starts above row slot 0,
+  // 1 = anything: the untouched slot's FMUL2 + D FFMA2 are not issued at all
+  auto point = [&](auto clc) {
+    constexpr int CLS = decltype(clc)::value;
+    constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
+    float2 wv[S][CX];
+#pragma unroll
+    for (int s = S0; s < S1; s++)
+#pragma unroll
+      for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
+    ax += RB; ay += RB; az += RB;
+    pr.load_xy(ax, ay);
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+#pragma unroll
+      for (int j = 4 * i; j < 4 * i + 4; j++) {
+        if (j < D) {
+          const float2 kzj = pr.kz(j);
+#pragma unroll
+          for (int s = S0; s < S1; s++)
+#pragma unroll
+            for (int c = 0; c < CX; c++) acc[s][c][j] = fma2(wv[s][c], kzj, acc[s][c][j]);
+        }
+      }
+      pr.load_kv(az, i);
+    }
+  };
+  auto sentinel = [&](int row) {  // META of all four y-block copies
+    if (lane < 4) reinterpret_cast<int *>(rows)[row * C::ROW + C::KYO + 4 * lane + 3] = SWR2_SENTINEL;
+  };
+
+  int cur = SWR_EMPTY;  // first (relative) plane held by the ring
+  int slot = 0;         // ring slot of plane cur = cur mod D
+  // Two-deep software pipeline over batches of 32 points (see k_swr_spread)
+  const PtRec<float> *recp = a.rec + first + lane;
+  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto ldc = [&](const float4 &rc, float2 &sc) {
+    const int o = __float_as_int(rc.w);
+    if (a.scale) sc = __ldg(a.scale + o);
+    return ld_stream2(cin + o);
+  };
+  const float2 zero2 = make_float2(0.f, 0.f);
+  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
+  float4 recB = lane + C::PB < cnt ? ld_stream4(recp + C::PB) : zrec;
+  float2 sA = make_float2(1.f, 0.f), sB = sA;
+  float2 cA = lane < cnt ? ldc(recA, sA) : zero2;
+  sentinel(C::PB);
+  for (int b0 = 0; b0 < cnt; b0 += C::PB) {
+    const int nb = min(C::PB, cnt - b0);
+    const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
+    const float2 cB = b0 + C::PB + lane < cnt ? ldc(recB, sB) : zero2;
+    __syncwarp();
+    int pos, cls;
+#if SWR_YCLASS
+    swr_batch_order<NS>(recA, nb, ya, lane, pos, cls);
+#else
+    pos = lane; cls = 1;
+#endif
+    if (lane < nb) {
+      float2 cv = cA;
+      if (a.scale) cv = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
+      swr2_weights<NS>(tab, recA, cv, xa, ya, zb, rows + pos * C::ROW, 0, cls);
+    }
+    if (nb < C::PB) sentinel(nb);
+    __syncwarp();
+    recA = recB;
+    recB = recC;
+    cA = cB;
+    sA = sB;
+    ax = ax0; ay = ay0; az = az0;
+    pr.load_all(ax, ay, az);
+    for (;;) {
+      int mt = pr.meta();
+      if (mt < 0) break;
+      const int z = mt >> 3;
+      if (z != cur) {
+        if (cur != SWR_EMPTY) {  // retire the planes below the new window (all D after a gap / disorder)
+          const unsigned d = (unsigned)(z - cur);
+          const int n = d >= (unsigned)D ? D : (int)d;
+          for (int i = 0; i < n; i++) {
+            retire(slot, cur);
+            slot = slot + 1 == D ? 0 : slot + 1;
+            cur++;
+          }
+        }
+        if (cur != z) {
+          cur = z;
+          slot = (int)((unsigned)z % (unsigned)D);
+        }
+      }
+      const int k0 = mt & ~3;
+      while (mt == k0) {
+        point(std::integral_constant<int, 0>{});
+        mt = pr.meta();
+      }
+      while (mt == k0 + 1) {
+        point(std::integral_constant<int, 1>{});
+        mt = pr.meta();
+      }
+      while (mt == k0 + 2) {
+        point(std::integral_constant<int, 2>{});
+        mt = pr.meta();
+      }
+    }
+  }
+  if (cur != SWR_EMPTY)
+    for (int i = 0; i < D; i++) {
+      retire(slot, cur);
+      slot = slot + 1 == D ? 0 : slot + 1;
+      cur++;
+    }
+}
+
+// ==================================================================================== INTERP
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
+    k_swr2_interp(const SwrArgs a, const __grid_constant__ HornerTable<float> tab) {
+  using C = Swr2Cfg<NS>;
+  constexpr int D = C::D, S = C::S, CX = C::CX, NV = C::NV;
+  extern __shared__ __align__(16) float swr_smem[];
+  const int lane = threadIdx.x;
+  int first, cnt, x0, y0, z0;
+  if (!swr2_decode(a, blockIdx.x, first, cnt, x0, y0, z0)) return;
+  float *rows = swr_smem;
+  float2 *RES = reinterpret_cast<float2 *>(swr_smem + C::RES_OFF);
+  float2 *res_w = RES + lane;                                        // + (t & 15) * 33 per point
+  const float2 *res_r = RES + (lane & 15) * 33 + (lane >> 4) * 16;  // this lane's 16 terms of a half-batch sum
+  int *opad = reinterpret_cast<int *>(RES + 32);  // pad column of RES: original index by batch position
+  float2 *cout = a.cout + (int64_t)blockIdx.y * a.M;
+
+  const int r = lane >> 3, q = lane & 7;
+  const int xa = x0 - C::H, ya = y0 - C::H, zb = z0 - C::H - C::ZBIAS;
+  const int nf0 = a.nf[0], nf1 = a.nf[1], nf2 = a.nf[2];
+  const int64_t pstride = (int64_t)nf0 * nf1;
+  const float2 *cell[S];  // this lane's cell of each row slot in plane 0
+#pragma unroll
+  for (int s = 0; s < S; s++)
+    cell[s] = a.fw + (int64_t)blockIdx.y * a.nftot +
+              (wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0));
+  auto plane_off = [&](int prel) {
+    int gz = prel + zb;
+    gz = gz < 0 ? gz + nf2 : gz;
+    if (gz >= nf2) gz = gz - nf2 < nf2 ? gz - nf2 : gz % nf2;
+    return (int64_t)gz * pstride;
+  };
+
+  float2 val[S][CX][D];  // ring of loaded planes, absolute slots
+  auto fetch = [&](int prel, float2 (&v)[S][CX]) {
+    const int64_t po = plane_off(prel);
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      if constexpr (CX == 1) {
+        v[s][0] = __ldg(cell[s] + po);
+      } else {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(cell[s] + po));
+        v[s][0] = make_float2(t.x, t.y);
+        v[s][1] = make_float2(t.z, t.w);
+      }
+    }
+  };
+  auto put = [&](int slot, const float2 (&v)[S][CX]) {
+    auto one = [&](auto kc) {
+      constexpr int K = decltype(kc)::value;
+      if constexpr (K < D) {
+#pragma unroll
+        for (int s = 0; s < S; s++)
+#pragma unroll
+          for (int c = 0; c < CX; c++) val[s][c][K] = v[s][c];
+      }
+    };
+    switch (slot) {
+      case 0: one(std::integral_constant<int, 0>{}); break;
+      case 1: one(std::integral_constant<int, 1>{}); break;
+      case 2: one(std::integral_constant<int, 2>{}); break;
+      case 3: one(std::integral_constant<int, 3>{}); break;
+      case 4: one(std::integral_constant<int, 4>{}); break;
+      case 5: one(std::integral_constant<int, 5>{}); break;
+      case 6: one(std::integral_constant<int, 6>{}); break;
+      default: one(std::integral_constant<int, 7>{}); break;
+    }
+  };
+#if SWR2_STAGE
+  // staging ring: stage g holds one plane, [s][lane] float2 (x CX); this lane only ever reads
+  // back what it copied itself, so cp.async.wait_group is all the synchronisation needed
+  float2 *stg = reinterpret_cast<float2 *>(swr_smem + C::STG_OFF) + lane * CX;
+  constexpr int STG_PLANE = S * 32 * CX;  // float2 per stage
+  int sg = 0;                             // stage that holds plane cur + D
+  const int plast = C::ZBIAS + C::BZ + D - 2;  // last relative plane a point of this bin can touch
+  auto stage_issue = [&](int g, int prel) {
+    if (prel <= plast) {
+      const int64_t po = plane_off(prel);
+#pragma unroll
+      for (int s = 0; s < S; s++) {
+        if constexpr (CX == 1) cp_async8(stg + g * STG_PLANE + s * 32 * CX, cell[s] + po);
+        else cp_async16(stg + g * STG_PLANE + s * 32 * CX, cell[s] + po);
+      }
+    }
+    cp_async_commit();  // (possibly empty) group: keeps one group per stage in flight
+  };
+  auto stage_read = [&](int g, float2 (&v)[S][CX]) {
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      if constexpr (CX == 1) {
+        v[s][0] = stg[g * STG_PLANE + s * 32 * CX];
+      } else {
+        const float4 t = *reinterpret_cast<const float4 *>(stg + g * STG_PLANE + s * 32 * CX);
+        v[s][0] = make_float2(t.x, t.y);
+        v[s][1] = make_float2(t.z, t.w);
+      }
+    }
+  };
+#else
+  float2 pre[S][CX];  // plane cur + D, fetched one ring step ahead
+#endif
+  // (re)load the whole ring for a window starting at relative plane p0
+  auto refill = [&](int p0) {
+    int sl = (int)((unsigned)p0 % (unsigned)D);
+#if SWR2_STAGE
+    cp_async_wait<0>();
+#endif
+    for (int k = 0; k < D; k++) {
+      float2 v[S][CX];
+      fetch(p0 + k, v);
+      put(sl, v);
+      sl = sl + 1 == D ? 0 : sl + 1;
+    }
+#if SWR2_STAGE
+    for (int g = 0; g < SWR2_STG; g++) stage_issue(g, p0 + D + g);
+    sg = 0;
+#else
+    fetch(p0 + D, pre);
+#endif
+  };
+
+  Swr2Row<NS> pr;
+  const unsigned ax0 = smem_u32(rows + C::KXO + 2 * CX * q), ay0 = smem_u32(rows + C::KYO + 4 * r),
+                 az0 = smem_u32(rows + C::KZO);
+  unsigned ax = ax0, ay = ay0, az = az0;
+  constexpr unsigned RB = C::ROW * sizeof(float);
+  auto sentinel = [&](int row) {  // META of all four y-block copies
+    if (lane < 4) reinterpret_cast<int *>(rows)[row * C::ROW + C::KYO + 4 * lane + 3] = SWR2_SENTINEL;
+  };
+  // interpolated value (this lane's share) of the point held in `pr`, then roll `pr` on to the next row
+  auto point = [&](auto clc) {
+    constexpr int CLS = decltype(clc)::value;
+    constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
+    float2 wv[S][CX];
+#pragma unroll
+    for (int s = S0; s < S1; s++)
+#pragma unroll
+      for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
+    ax += RB; ay += RB; az += RB;
+    pr.load_xy(ax, ay);
+    float2 part[S][CX];
+    bool started = false;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+#pragma unroll
+      for (int j = 4 * i; j < 4 * i + 4; j++) {
+        if (j < D) {
+          const float2 kzj = pr.kz(j);
+#pragma unroll
+          for (int s = S0; s < S1; s++)
+#pragma unroll
+            for (int c = 0; c < CX; c++)
+              part[s][c] = !started ? mul2(val[s][c][j], kzj) : fma2(val[s][c][j], kzj, part[s][c]);
+          started = true;
+        }
+      }
+      pr.load_kv(az, i);
+    }
+    float2 res = mul2(part[S0][0], wv[S0][0]);
+#pragma unroll
+    for (int s = S0; s < S1; s++)
+#pragma unroll
+      for (int c = 0; c < CX; c++)
+        if (s - S0 + c > 0) res = fma2(part[s][c], wv[s][c], res);
+    return res;
+  };
+
+  int cur = SWR_EMPTY;  // first (relative) plane held by the ring
+  int slot = 0;         // ring slot of plane cur
+  const PtRec<float> *recp = a.rec + first + lane;
+  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
+  sentinel(C::PB);
+  for (int b0 = 0; b0 < cnt; b0 += C::PB) {
+    const int nb = min(C::PB, cnt - b0);
+    const float4 recB = b0 + C::PB + lane < cnt ? ld_stream4(recp + b0 + C::PB) : zrec;
+    float2 mine = make_float2(0.f, 0.f);  // interpolated value of the point at batch position `lane`
+    __syncwarp();
+    int pos, cls;
+#if SWR2_YCLASS_INTERP
+    swr_batch_order<NS>(recA, nb, ya, lane, pos, cls);
+#else
+    pos = lane; cls = 1;
+#endif
+    if (lane < nb) {
+      opad[(pos & 15) * 66 + (pos >> 4)] = __float_as_int(recA.w);
+      swr2_weights<NS>(tab, recA, make_float2(1.f, 1.f), xa, ya, zb, rows + pos * C::ROW, pos >> 4, cls);
+    }
+    if (nb < C::PB) sentinel(nb);
+    __syncwarp();
+    const int orig = lane < nb ? opad[(lane & 15) * 66 + (lane >> 4)] : 0;
+    recA = recB;
+    ax = ax0; ay = ay0; az = az0;
+    pr.load_all(ax, ay, az);
+    int half = 0;
+    float2 *rw = res_w;
+    for (;;) {
+      int mt = pr.meta();
+      const int h = mt < 0 ? 2 : ((mt >> 2) & 1);
+      if (h != half) {
+        // lane (row, part) sums half of row `row`; one butterfly step finishes it.  Point
+        // 16 * half + row belongs to lane 16 * half + row = the lane with part == half.
+        __syncwarp();
+        float2 s0 = res_r[0];
+#pragma unroll
+        for (int j = 1; j < 16; j++) s0 = add2(s0, res_r[j]);
+        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);
+        s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);
+        if ((lane >> 4) == half) mine = s0;
+        __syncwarp();
+        if (mt < 0) break;
+        half = h;
+        rw = res_w;
+      }
+      const int z = mt >> 3;
+      if (z != cur) {
+        const unsigned d = cur == SWR_EMPTY ? (unsigned)D : (unsigned)(z - cur);
+        // first point, a gap wider than the ring, disorder, or a window that leaves the bin's
+        // planes (never for folded coordinates; the staging ring does not fetch beyond them)
+        if (d >= (unsigned)D || z > C::ZBIAS + C::BZ - 1) {
+          refill(z);
+          cur = z;
+          slot = (int)((unsigned)z % (unsigned)D);
+        } else {
+          for (unsigned i = 0; i < d; i++) {  // slot of plane cur takes plane cur + D
+            float2 v[S][CX];
+#if SWR2_STAGE
+            cp_async_wait<SWR2_STG - 1>();
+            stage_read(sg, v);
+            put(slot, v);
+            stage_issue(sg, cur + D + SWR2_STG);
+            sg = sg + 1 == SWR2_STG ? 0 : sg + 1;
+#else
+#pragma unroll
+            for (int s = 0; s < S; s++)
+#pragma unroll
+              for (int c = 0; c < CX; c++) v[s][c] = pre[s][c];
+            put(slot, v);
+            fetch(cur + D + 1, pre);
+            if (SWR2_PF > 0) {
+              const int64_t po = plane_off(cur + D + 1 + SWR2_PF);
+#pragma unroll
+              for (int s = 0; s < S; s++) prefetch_l2(cell[s] + po);
+            }
+#endif
+            slot = slot + 1 == D ? 0 : slot + 1;
+            cur++;
+          }
+        }
+      }
+      const int k0 = mt & ~3;
+      while (mt == k0) {
+        *rw = point(std::integral_constant<int, 0>{});
+        rw += 33;
+        mt = pr.meta();
+      }
+      while (mt == k0 + 1) {
+        *rw = point(std::integral_constant<int, 1>{});
+        rw += 33;
+        mt = pr.meta();
+      }
+      while (mt == k0 + 2) {
+        *rw = point(std::integral_constant<int, 2>{});
+        rw += 33;
+        mt = pr.meta();
+      }
+    }
+    if (lane < nb) {
+      float2 o = mine;
+      if (a.scale) {
+        const float2 sc = __ldg(a.scale + orig);
+        o = make_float2(o.x * sc.x - o.y * sc.y, o.x * sc.y + o.y * sc.x);
+      }
+      cout[orig] = o;
+    }
+  }
+#if SWR2_STAGE
+  cp_async_wait<0>();
+#endif
+}
+
+}  // namespace b2n
