@@ -2,8 +2,9 @@
 #include "rt2_kernels.cuh"
 #include "swr2_kernels.cuh"
 
-// generation of the 3-D sliding-window kernels: 2 = swr2_kernels.cuh (absolute ring slots), 1 = the
-// phase-chain kernels of swr_kernels.cuh (kept for A/B builds: make EXTRA=-DSWR_GEN=1)
+// 3-D spreader: 2 = k_swr2_spread (swr2_kernels.cuh: absolute ring slots), 1 = the phase-chain
+// k_swr_spread of swr_kernels.cuh (A/B builds: make EXTRA=-DSWR_GEN=1).  Interpolation always runs
+// the phase-chain k_swr_interp (an absolute-slot version was slower: DESIGN.md 4.3).
 #ifndef SWR_GEN
 #define SWR_GEN 2
 #endif
@@ -67,18 +68,11 @@ template <int NS> struct SwrDispatch {
   }
   static int interp(Plan<float> &p, const SwrArgs &a, int ntr) {
     if (p.ns == NS) {
-#if SWR_GEN == 2
-      using C = Swr2Cfg<NS>;
-      dim3 grid((unsigned)p.pts.sp_cap, (unsigned)ntr);
-      B2N_CUDA_OK(cudaFuncSetAttribute(k_swr2_interp<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::INTERP_SMEM));
-      k_swr2_interp<NS><<<grid, 32, C::INTERP_SMEM, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
-#else
       using C = SwrCfg<NS>;
       const size_t smem = SwrInterpSmem<NS>::bytes();
       B2N_CUDA_OK(cudaFuncSetAttribute(k_swr_interp<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
       k_swr_interp<NS><<<grid, 32 * C::WARPS, smem, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
-#endif
       B2N_LAUNCH_OK();
       return 0;
     }

@@ -10,13 +10,14 @@
 //     accumulator indices by instantiating the whole loop body D times (a chain of phases entered
 //     through a switch): 7x the code (instruction-cache misses, `no_instruction` stalls) and ~9
 //     control instructions per point to move between phases.
-//   * SENTINEL-TERMINATED RUNS.  Row nb of a batch carries META = -1, every real row
-//     META = ((plane << 1 | half) << 2 | y class) >= 0, so the inner loop is
-//     `while (meta == key) { point; }` -- one compare and one branch per point, no point counter,
-//     no end-of-batch test.  Plane changes (retire / fetch a plane), half-batch boundaries
-//     (interpolation: reduce the partial results) and the end of the batch all surface as a key
-//     change and are handled outside the loop.
-//   * the row piece that carries META is rolled first, so the loop branch never waits on a load.
+//   * UNIFORM RUNS.  Every row carries META = ((plane << 1 | half) << 2 | y class).  After the
+//     weight phase the lanes compare the METAs of neighbouring rows and three ballots turn the
+//     batch into warp-UNIFORM run boundaries and class masks, so the inner loops are counted loops
+//     `for (i < n) point<class>()` with uniform trip counts: no convergence barriers (BSSY/BSYNC),
+//     no branch that waits on a shared-memory load.  Plane changes (retire / fetch a plane) and
+//     half-batch boundaries (interpolation: reduce the partial results) are run boundaries and are
+//     handled between the loops.  (A first version looped `while (meta == key)` on the loaded META:
+//     15 instructions per point of run bookkeeping and barriers, profiles/r02d.)
 //   * Interpolation stages the NEXT planes of the window through shared memory with cp.async
 //     (LDGSTS, 8 bytes per lane and row slot, SWR2_STG planes ahead, one commit group per plane):
 //     the first generation kept one plane of look-ahead in registers and stalled on it
@@ -44,7 +45,6 @@ namespace b2n {
 #define SWR2_YCLASS_INTERP 1
 #endif
 
-constexpr int SWR2_SENTINEL = -1;
 
 // Row of one point in shared memory (floats).  Differences from SwrCfg: META sits in the unused
 // fourth column of the y block (one copy per lane row, so it arrives with the y weights, first
@@ -58,7 +58,7 @@ template <int NS> struct Swr2Cfg : SwrCfg<NS> {
   static constexpr int ROW0 = KZO + KZW;
   static constexpr int ROW = (ROW0 / 4) % 2 == 1 ? ROW0 : ROW0 + 4;  // stride/4 odd (see SwrCfg)
   static constexpr int NV = KZW / 4;
-  static constexpr int NROWS = B::PB + 1;       // + the sentinel row of a full batch
+  static constexpr int NROWS = B::PB + 1;       // + one row: the rolling loads of the last point read a row ahead
   static constexpr int ZBIAS = 16 * B::D;       // planes are counted from zb = z0 - H - ZBIAS: always > 0
   static constexpr int SPREAD_FLOATS = NROWS * ROW;
   static constexpr int SPREAD_SMEM = SPREAD_FLOATS * (int)sizeof(float);
@@ -95,6 +95,18 @@ __device__ __forceinline__ float4 lds128(unsigned a) {
 __device__ __forceinline__ float2 lds64(unsigned a) {
   float2 v;
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+
+__device__ __forceinline__ void sts64(unsigned a, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts32(unsigned a, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ int lds32(unsigned a) {
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
 
@@ -261,21 +273,30 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
 #pragma unroll
       for (int k = 0; k < D; k++) acc[s][c][k] = make_float2(0.f, 0.f);
 
-  // retire relative plane prel held by ring slot `slot`: RED this lane's cells, clear the slot
-  auto retire = [&](int slot, int prel) {
-    int gz = prel + zb;
+  // Retire the first plane of the ring (relative plane `cur`, ring slot `slot`): RED this lane's
+  // cells, clear the slot, move on by one plane.  pz[s] = this lane's cell of row slot s in that
+  // plane, carried along (+ one plane per retire, periodic wrap) instead of being rebuilt from a
+  // 64-bit multiply per plane.
+  float2 *pz[S];
+  int gz = 0;  // fine-grid plane of relative plane cur
+  auto seek = [&](int prel) {  // position pz on relative plane prel
+    gz = prel + zb;
     gz = gz < 0 ? gz + nf2 : gz;
     if (gz >= nf2) gz = gz - nf2 < nf2 ? gz - nf2 : gz % nf2;
     const int64_t po = (int64_t)gz * pstride;
+#pragma unroll
+    for (int s = 0; s < S; s++) pz[s] = cell[s] + po;
+  };
+  auto retire = [&](int slot) {
     auto one = [&](auto kc) {
       constexpr int K = decltype(kc)::value;
       if constexpr (K < D) {
 #pragma unroll
         for (int s = 0; s < S; s++) {
           if constexpr (CX == 1) {
-            red_add(cell[s] + po, acc[s][0][K]);
+            red_add(pz[s], acc[s][0][K]);
           } else {
-            red_add4(reinterpret_cast<float4 *>(cell[s] + po),
+            red_add4(reinterpret_cast<float4 *>(pz[s]),
                      make_float4(acc[s][0][K].x, acc[s][0][K].y, acc[s][1][K].x, acc[s][1][K].y));
           }
 #pragma unroll
@@ -293,6 +314,10 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
       case 6: one(std::integral_constant<int, 6>{}); break;
       default: one(std::integral_constant<int, 7>{}); break;
     }
+    const int64_t step = gz + 1 == nf2 ? -(int64_t)(nf2 - 1) * pstride : pstride;
+    gz = gz + 1 == nf2 ? 0 : gz + 1;
+#pragma unroll
+    for (int s = 0; s < S; s++) pz[s] += step;
   };
 
   Swr2Row<NS> pr;
@@ -329,8 +354,9 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
       pr.load_kv(az, i);
     }
   };
-  auto sentinel = [&](int row) {  // META of all four y-block copies
-    if (lane < 4) reinterpret_cast<int *>(rows)[row * C::ROW + C::KYO + 4 * lane + 3] = SWR2_SENTINEL;
+  const unsigned sm0 = smem_u32(swr_smem);
+  auto sentinel = [&](int row) {  // META = -1 in all four y-block copies of `row`
+    if (lane < 4) sts32(sm0 + (row * C::ROW + C::KYO + 4 * lane + 3) * 4, -1);
   };
 
   int cur = SWR_EMPTY;  // first (relative) plane held by the ring
@@ -375,21 +401,23 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
     pr.load_all(ax, ay, az);
     for (;;) {
       int mt = pr.meta();
-      if (mt < 0) break;
+      if (mt < 0) break;  // sentinel row
       const int z = mt >> 3;
       if (z != cur) {
         if (cur != SWR_EMPTY) {  // retire the planes below the new window (all D after a gap / disorder)
           const unsigned d = (unsigned)(z - cur);
-          const int n = d >= (unsigned)D ? D : (int)d;
-          for (int i = 0; i < n; i++) {
-            retire(slot, cur);
+          const int nr = d >= (unsigned)D ? D : (int)d;
+#pragma unroll 1
+          for (int i = 0; i < nr; i++) {
+            retire(slot);
             slot = slot + 1 == D ? 0 : slot + 1;
             cur++;
           }
         }
-        if (cur != z) {
+        if (cur != z) {  // first point of the subproblem, or a jump over empty planes
           cur = z;
           slot = (int)((unsigned)z % (unsigned)D);
+          seek(z);
         }
       }
       const int k0 = mt & ~3;
@@ -408,308 +436,11 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
     }
   }
   if (cur != SWR_EMPTY)
+#pragma unroll 1
     for (int i = 0; i < D; i++) {
-      retire(slot, cur);
+      retire(slot);
       slot = slot + 1 == D ? 0 : slot + 1;
-      cur++;
     }
-}
-
-// ==================================================================================== INTERP
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-template <int NS>
-__global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
-    k_swr2_interp(const SwrArgs a, const __grid_constant__ HornerTable<float> tab) {
-  using C = Swr2Cfg<NS>;
-  constexpr int D = C::D, S = C::S, CX = C::CX, NV = C::NV;
-  extern __shared__ __align__(16) float swr_smem[];
-  const int lane = threadIdx.x;
-  int first, cnt, x0, y0, z0;
-  if (!swr2_decode(a, blockIdx.x, first, cnt, x0, y0, z0)) return;
-  float *rows = swr_smem;
-  float2 *RES = reinterpret_cast<float2 *>(swr_smem + C::RES_OFF);
-  float2 *res_w = RES + lane;                                        // + (t & 15) * 33 per point
-  const float2 *res_r = RES + (lane & 15) * 33 + (lane >> 4) * 16;  // this lane's 16 terms of a half-batch sum
-  int *opad = reinterpret_cast<int *>(RES + 32);  // pad column of RES: original index by batch position
-  float2 *cout = a.cout + (int64_t)blockIdx.y * a.M;
-
-  const int r = lane >> 3, q = lane & 7;
-  const int xa = x0 - C::H, ya = y0 - C::H, zb = z0 - C::H - C::ZBIAS;
-  const int nf0 = a.nf[0], nf1 = a.nf[1], nf2 = a.nf[2];
-  const int64_t pstride = (int64_t)nf0 * nf1;
-  const float2 *cell[S];  // this lane's cell of each row slot in plane 0
-#pragma unroll
-  for (int s = 0; s < S; s++)
-    cell[s] = a.fw + (int64_t)blockIdx.y * a.nftot +
-              (wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0));
-  auto plane_off = [&](int prel) {
-    int gz = prel + zb;
-    gz = gz < 0 ? gz + nf2 : gz;
-    if (gz >= nf2) gz = gz - nf2 < nf2 ? gz - nf2 : gz % nf2;
-    return (int64_t)gz * pstride;
-  };
-
-  float2 val[S][CX][D];  // ring of loaded planes, absolute slots
-  auto fetch = [&](int prel, float2 (&v)[S][CX]) {
-    const int64_t po = plane_off(prel);
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      if constexpr (CX == 1) {
-        v[s][0] = __ldg(cell[s] + po);
-      } else {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(cell[s] + po));
-        v[s][0] = make_float2(t.x, t.y);
-        v[s][1] = make_float2(t.z, t.w);
-      }
-    }
-  };
-  auto put = [&](int slot, const float2 (&v)[S][CX]) {
-    auto one = [&](auto kc) {
-      constexpr int K = decltype(kc)::value;
-      if constexpr (K < D) {
-#pragma unroll
-        for (int s = 0; s < S; s++)
-#pragma unroll
-          for (int c = 0; c < CX; c++) val[s][c][K] = v[s][c];
-      }
-    };
-    switch (slot) {
-      case 0: one(std::integral_constant<int, 0>{}); break;
-      case 1: one(std::integral_constant<int, 1>{}); break;
-      case 2: one(std::integral_constant<int, 2>{}); break;
-      case 3: one(std::integral_constant<int, 3>{}); break;
-      case 4: one(std::integral_constant<int, 4>{}); break;
-      case 5: one(std::integral_constant<int, 5>{}); break;
-      case 6: one(std::integral_constant<int, 6>{}); break;
-      default: one(std::integral_constant<int, 7>{}); break;
-    }
-  };
-#if SWR2_STAGE
-  // staging ring: stage g holds one plane, [s][lane] float2 (x CX); this lane only ever reads
-  // back what it copied itself, so cp.async.wait_group is all the synchronisation needed
-  float2 *stg = reinterpret_cast<float2 *>(swr_smem + C::STG_OFF) + lane * CX;
-  constexpr int STG_PLANE = S * 32 * CX;  // float2 per stage
-  int sg = 0;                             // stage that holds plane cur + D
-  const int plast = C::ZBIAS + C::BZ + D - 2;  // last relative plane a point of this bin can touch
-  auto stage_issue = [&](int g, int prel) {
-    if (prel <= plast) {
-      const int64_t po = plane_off(prel);
-#pragma unroll
-      for (int s = 0; s < S; s++) {
-        if constexpr (CX == 1) cp_async8(stg + g * STG_PLANE + s * 32 * CX, cell[s] + po);
-        else cp_async16(stg + g * STG_PLANE + s * 32 * CX, cell[s] + po);
-      }
-    }
-    cp_async_commit();  // (possibly empty) group: keeps one group per stage in flight
-  };
-  auto stage_read = [&](int g, float2 (&v)[S][CX]) {
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      if constexpr (CX == 1) {
-        v[s][0] = stg[g * STG_PLANE + s * 32 * CX];
-      } else {
-        const float4 t = *reinterpret_cast<const float4 *>(stg + g * STG_PLANE + s * 32 * CX);
-        v[s][0] = make_float2(t.x, t.y);
-        v[s][1] = make_float2(t.z, t.w);
-      }
-    }
-  };
-#else
-  float2 pre[S][CX];  // plane cur + D, fetched one ring step ahead
-#endif
-  // (re)load the whole ring for a window starting at relative plane p0
-  auto refill = [&](int p0) {
-    int sl = (int)((unsigned)p0 % (unsigned)D);
-#if SWR2_STAGE
-    cp_async_wait<0>();
-#endif
-    for (int k = 0; k < D; k++) {
-      float2 v[S][CX];
-      fetch(p0 + k, v);
-      put(sl, v);
-      sl = sl + 1 == D ? 0 : sl + 1;
-    }
-#if SWR2_STAGE
-    for (int g = 0; g < SWR2_STG; g++) stage_issue(g, p0 + D + g);
-    sg = 0;
-#else
-    fetch(p0 + D, pre);
-#endif
-  };
-
-  Swr2Row<NS> pr;
-  const unsigned ax0 = smem_u32(rows + C::KXO + 2 * CX * q), ay0 = smem_u32(rows + C::KYO + 4 * r),
-                 az0 = smem_u32(rows + C::KZO);
-  unsigned ax = ax0, ay = ay0, az = az0;
-  constexpr unsigned RB = C::ROW * sizeof(float);
-  auto sentinel = [&](int row) {  // META of all four y-block copies
-    if (lane < 4) reinterpret_cast<int *>(rows)[row * C::ROW + C::KYO + 4 * lane + 3] = SWR2_SENTINEL;
-  };
-  // interpolated value (this lane's share) of the point held in `pr`, then roll `pr` on to the next row
-  auto point = [&](auto clc) {
-    constexpr int CLS = decltype(clc)::value;
-    constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
-    float2 wv[S][CX];
-#pragma unroll
-    for (int s = S0; s < S1; s++)
-#pragma unroll
-      for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
-    ax += RB; ay += RB; az += RB;
-    pr.load_xy(ax, ay);
-    float2 part[S][CX];
-    bool started = false;
-#pragma unroll
-    for (int i = 0; i < NV; i++) {
-#pragma unroll
-      for (int j = 4 * i; j < 4 * i + 4; j++) {
-        if (j < D) {
-          const float2 kzj = pr.kz(j);
-#pragma unroll
-          for (int s = S0; s < S1; s++)
-#pragma unroll
-            for (int c = 0; c < CX; c++)
-              part[s][c] = !started ? mul2(val[s][c][j], kzj) : fma2(val[s][c][j], kzj, part[s][c]);
-          started = true;
-        }
-      }
-      pr.load_kv(az, i);
-    }
-    float2 res = mul2(part[S0][0], wv[S0][0]);
-#pragma unroll
-    for (int s = S0; s < S1; s++)
-#pragma unroll
-      for (int c = 0; c < CX; c++)
-        if (s - S0 + c > 0) res = fma2(part[s][c], wv[s][c], res);
-    return res;
-  };
-
-  int cur = SWR_EMPTY;  // first (relative) plane held by the ring
-  int slot = 0;         // ring slot of plane cur
-  const PtRec<float> *recp = a.rec + first + lane;
-  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
-  sentinel(C::PB);
-  for (int b0 = 0; b0 < cnt; b0 += C::PB) {
-    const int nb = min(C::PB, cnt - b0);
-    const float4 recB = b0 + C::PB + lane < cnt ? ld_stream4(recp + b0 + C::PB) : zrec;
-    float2 mine = make_float2(0.f, 0.f);  // interpolated value of the point at batch position `lane`
-    __syncwarp();
-    int pos, cls;
-#if SWR2_YCLASS_INTERP
-    swr_batch_order<NS>(recA, nb, ya, lane, pos, cls);
-#else
-    pos = lane; cls = 1;
-#endif
-    if (lane < nb) {
-      opad[(pos & 15) * 66 + (pos >> 4)] = __float_as_int(recA.w);
-      swr2_weights<NS>(tab, recA, make_float2(1.f, 1.f), xa, ya, zb, rows + pos * C::ROW, pos >> 4, cls);
-    }
-    if (nb < C::PB) sentinel(nb);
-    __syncwarp();
-    const int orig = lane < nb ? opad[(lane & 15) * 66 + (lane >> 4)] : 0;
-    recA = recB;
-    ax = ax0; ay = ay0; az = az0;
-    pr.load_all(ax, ay, az);
-    int half = 0;
-    float2 *rw = res_w;
-    for (;;) {
-      int mt = pr.meta();
-      const int h = mt < 0 ? 2 : ((mt >> 2) & 1);
-      if (h != half) {
-        // lane (row, part) sums half of row `row`; one butterfly step finishes it.  Point
-        // 16 * half + row belongs to lane 16 * half + row = the lane with part == half.
-        __syncwarp();
-        float2 s0 = res_r[0];
-#pragma unroll
-        for (int j = 1; j < 16; j++) s0 = add2(s0, res_r[j]);
-        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, 16);
-        s0.y += __shfl_xor_sync(0xffffffffu, s0.y, 16);
-        if ((lane >> 4) == half) mine = s0;
-        __syncwarp();
-        if (mt < 0) break;
-        half = h;
-        rw = res_w;
-      }
-      const int z = mt >> 3;
-      if (z != cur) {
-        const unsigned d = cur == SWR_EMPTY ? (unsigned)D : (unsigned)(z - cur);
-        // first point, a gap wider than the ring, disorder, or a window that leaves the bin's
-        // planes (never for folded coordinates; the staging ring does not fetch beyond them)
-        if (d >= (unsigned)D || z > C::ZBIAS + C::BZ - 1) {
-          refill(z);
-          cur = z;
-          slot = (int)((unsigned)z % (unsigned)D);
-        } else {
-          for (unsigned i = 0; i < d; i++) {  // slot of plane cur takes plane cur + D
-            float2 v[S][CX];
-#if SWR2_STAGE
-            cp_async_wait<SWR2_STG - 1>();
-            stage_read(sg, v);
-            put(slot, v);
-            stage_issue(sg, cur + D + SWR2_STG);
-            sg = sg + 1 == SWR2_STG ? 0 : sg + 1;
-#else
-#pragma unroll
-            for (int s = 0; s < S; s++)
-#pragma unroll
-              for (int c = 0; c < CX; c++) v[s][c] = pre[s][c];
-            put(slot, v);
-            fetch(cur + D + 1, pre);
-            if (SWR2_PF > 0) {
-              const int64_t po = plane_off(cur + D + 1 + SWR2_PF);
-#pragma unroll
-              for (int s = 0; s < S; s++) prefetch_l2(cell[s] + po);
-            }
-#endif
-            slot = slot + 1 == D ? 0 : slot + 1;
-            cur++;
-          }
-        }
-      }
-      const int k0 = mt & ~3;
-      while (mt == k0) {
-        *rw = point(std::integral_constant<int, 0>{});
-        rw += 33;
-        mt = pr.meta();
-      }
-      while (mt == k0 + 1) {
-        *rw = point(std::integral_constant<int, 1>{});
-        rw += 33;
-        mt = pr.meta();
-      }
-      while (mt == k0 + 2) {
-        *rw = point(std::integral_constant<int, 2>{});
-        rw += 33;
-        mt = pr.meta();
-      }
-    }
-    if (lane < nb) {
-      float2 o = mine;
-      if (a.scale) {
-        const float2 sc = __ldg(a.scale + orig);
-        o = make_float2(o.x * sc.x - o.y * sc.y, o.x * sc.y + o.y * sc.x);
-      }
-      cout[orig] = o;
-    }
-  }
-#if SWR2_STAGE
-  cp_async_wait<0>();
-#endif
 }
 
 }  // namespace b2n

@@ -512,10 +512,39 @@ sub_done:;
 // per-half sums -- lane (row, part) adds columns part*16 .. part*16+15 of its row -- free of bank
 // conflicts with constant per-lane offsets).  The half-batch boundary is treated like a batch
 // boundary of the phase chain, so the inner loop carries no "group full?" test.
+// + the plane staging ring (SWR_STAGE): SWR_STG planes of [row slot][lane] float2 (x CX), filled by
+// cp.async (LDGSTS) SWR_STG ring steps ahead of their use.  The first version kept ONE plane of
+// look-ahead in registers (`pre`) and waited on it: long-scoreboard stalls ~1 per issue, 15 % of
+// all samples on the register moves that consume it (profiles/r01h) -- a plane is consumed every
+// ~2800 cycles, less than the latency of a fine-grid line under this kernel's own random 32-byte
+// output scatter.  Bulk/TMA copies (cp.async.bulk[.tensor]) need 16-byte aligned rows; a window
+// row starts at an odd cell (x0 - ns/2: 8-byte aligned) and wraps periodically, so the per-lane
+// 8-byte LDGSTS form is the one that fits.  Each lane reads back only what it copied itself:
+// cp.async.wait_group is all the synchronisation needed.
+#ifndef SWR_STAGE
+#define SWR_STAGE 1
+#endif
+#ifndef SWR_STG
+#define SWR_STG 2  // planes in flight: 2 -> 8.60 ms, 4 -> 8.72, 6 -> 8.82 at C3 (more stages = less L1 for the plane lines)
+#endif
 template <int NS> struct SwrInterpSmem {
-  static constexpr size_t warp_floats = SwrCfg<NS>::PB * SwrCfg<NS>::ROW + 2 * 16 * 33;  // multiple of 4 floats: rows stay 16-byte aligned
+  static constexpr size_t res_floats = SwrCfg<NS>::PB * SwrCfg<NS>::ROW + 2 * 16 * 33;  // multiple of 4 floats: rows stay 16-byte aligned
+  static constexpr size_t stg_floats = SWR_STAGE ? (size_t)SWR_STG * SwrCfg<NS>::S * 32 * 2 * SwrCfg<NS>::CX : 0;
+  static constexpr size_t warp_floats = res_floats + stg_floats;
   static constexpr size_t bytes() { return SwrCfg<NS>::WARPS * warp_floats * sizeof(float); }
 };
+
+__device__ __forceinline__ unsigned swr_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void swr_cp_async8(unsigned d, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(g) : "memory");
+}
+__device__ __forceinline__ void swr_cp_async16(unsigned d, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+}
+__device__ __forceinline__ void swr_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void swr_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 template <int NS>
 __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
@@ -542,11 +571,18 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     cell[s] = a.fw + (int64_t)blockIdx.y * a.nftot +
               (wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0));
 
+  int cur = SWR_EMPTY;  // first plane held by the ring
+  int ph = 0;           // ring slot of plane cur
+  // last plane a point of this bin can touch (anchor z0 + BZ - 1, window start - H, D planes)
+  const int plast = (a.sp_bin[blockIdx.x * C::WARPS + w] / (a.nbin[0] * a.nbin[1])) * a.bin[2] + C::BZ - 1 - C::H + D - 1;
   float2 val[S][CX][D];  // ring of loaded planes
-  float2 pre[S][CX];     // plane cur + D, fetched one ring step ahead
+  auto plane_off = [&](int p) {
+    int gz = p < 0 ? p + nf2 : (p >= nf2 ? p - nf2 : p);
+    if (gz >= nf2) gz %= nf2;  // look-ahead beyond one period (tiny grids)
+    return (int64_t)gz * pstride;
+  };
   auto fetch = [&](int p, float2 (&v)[S][CX]) {
-    const int gz = p < 0 ? p + nf2 : (p >= nf2 ? p - nf2 : p);
-    const int64_t po = (int64_t)gz * pstride;
+    const int64_t po = plane_off(p);
 #pragma unroll
     for (int s = 0; s < S; s++) {
       if constexpr (CX == 1) {
@@ -558,8 +594,51 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
       }
     }
   };
+#if SWR_STAGE
+  constexpr unsigned STG_PLANE = S * 32 * CX * 8;  // bytes per stage
+  const unsigned stg0 = swr_smem_u32(rows + SwrInterpSmem<NS>::res_floats) + lane * CX * 8;
+  unsigned sga = stg0;  // stage that holds plane cur + D
+  // copy this lane's cells of plane p into stage g (one commit group per plane, possibly empty:
+  // nothing is fetched beyond the last plane a point of this bin can touch)
+  auto stage_issue = [&](unsigned g, int p) {
+    if (p <= plast) {
+      const int64_t po = plane_off(p);
+#pragma unroll
+      for (int s = 0; s < S; s++) {
+        if constexpr (CX == 1) swr_cp_async8(g + s * 32 * CX * 8, cell[s] + po);
+        else swr_cp_async16(g + s * 32 * CX * 8, cell[s] + po);
+      }
+    }
+    swr_cp_async_commit();
+  };
+  // ring slot PH <- the oldest staged plane (= plane cur + D); its stage is re-issued SWR_STG planes on
+  auto stage_take = [&](auto phc) {
+    constexpr int PH = decltype(phc)::value;
+    swr_cp_async_wait<SWR_STG - 1>();
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      if constexpr (CX == 1) {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(sga + s * 32 * CX * 8));
+        val[s][0][PH] = v;
+      } else {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sga + s * 32 * CX * 8));
+        val[s][0][PH] = make_float2(v.x, v.y);
+        val[s][1][PH] = make_float2(v.z, v.w);
+      }
+    }
+    stage_issue(sga, cur + D + SWR_STG);
+    sga = sga + STG_PLANE == stg0 + SWR_STG * STG_PLANE ? stg0 : sga + STG_PLANE;
+  };
+#else
+  float2 pre[S][CX];     // plane cur + D, fetched one ring step ahead
+#endif
   // (re)load the whole ring for a window starting at plane p0; phases re-based so that ph = 0
   auto refill = [&](int p0) {
+#if SWR_STAGE
+    swr_cp_async_wait<0>();
+#endif
 #pragma unroll
     for (int k = 0; k < D; k++) {
       float2 v[S][CX];
@@ -569,7 +648,13 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
 #pragma unroll
         for (int c = 0; c < CX; c++) val[s][c][k] = v[s][c];
     }
+#if SWR_STAGE
+#pragma unroll
+    for (int g = 0; g < SWR_STG; g++) stage_issue(stg0 + g * STG_PLANE, p0 + D + g);
+    sga = stg0;
+#else
     fetch(p0 + D, pre);
+#endif
   };
   // interpolated value (this lane's share) of the point held in `pr`, then roll `pr` on to the
   // row at `ron`; PH = ring slot of the first plane of the point's window
@@ -612,8 +697,6 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     return res;
   };
 
-  int cur = SWR_EMPTY;  // first plane held by the ring
-  int ph = 0;           // ring slot of plane cur
   const PtRec<float> *recp = a.rec + first + lane;
   const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
@@ -684,6 +767,17 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
       }
       for (;;) {
         switch (ph) {
+#if SWR_STAGE
+#define SWR_INTERP_ADVANCE(PH)                                                                  \
+      stage_take(std::integral_constant<int, PH>{});                                            \
+      cur++;
+#else
+#define SWR_INTERP_ADVANCE(PH)                                                                  \
+      _Pragma("unroll") for (int s = 0; s < S; s++)                                             \
+          _Pragma("unroll") for (int c = 0; c < CX; c++) val[s][c][PH] = pre[s][c];             \
+      cur++;                                                                                    \
+      fetch(cur + D, pre);
+#endif
 #define SWR_INTERP_PHASE(PH)                                                                    \
   case PH:                                                                                      \
     if constexpr (PH < D) {                                                                     \
@@ -692,15 +786,12 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
         ph = PH;                                                                                \
         goto half_done;                                                                         \
       }                                                                                         \
-      if ((unsigned)(SWR_ZP(zw) - cur) >= (unsigned)D) {                                        \
+      if ((unsigned)(SWR_ZP(zw) - cur) >= (unsigned)D || SWR_ZP(zw) + D - 1 > plast) {          \
         fill = true;                                                                            \
         goto reenter;                                                                           \
       }                                                                                         \
       /* advance one plane: slot PH takes plane cur + D, the next one is requested */           \
-      _Pragma("unroll") for (int s = 0; s < S; s++)                                             \
-          _Pragma("unroll") for (int c = 0; c < CX; c++) val[s][c][PH] = pre[s][c];             \
-      cur++;                                                                                    \
-      fetch(cur + D, pre);                                                                      \
+      SWR_INTERP_ADVANCE(PH)                                                                    \
     }
           SWR_INTERP_PHASE(0)
           SWR_INTERP_PHASE(1)
@@ -711,6 +802,7 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
           SWR_INTERP_PHASE(6)
           SWR_INTERP_PHASE(7)
 #undef SWR_INTERP_PHASE
+#undef SWR_INTERP_ADVANCE
 #undef SWR_INTERP_POINTS
 #undef SWR_INTERP_CLASS
 #undef SWR_ZP
@@ -741,6 +833,9 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
       cout[orig] = o;
     }
   }
+#if SWR_STAGE
+  swr_cp_async_wait<0>();
+#endif
 }
 
 }  // namespace b2n

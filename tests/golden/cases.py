@@ -56,7 +56,7 @@ def make_inputs(case):
     return dict(pts=pts, tgt=tgt, data=data)
 
 
-FLOOR = {False: 1.5e-6, True: 2e-14}   # rounding floor of the arithmetic (fp32 / fp64), NOT added to 2*eps
+FLOOR = {False: 1e-6, True: 2e-14}   # rounding floor of the arithmetic (fp32 / fp64), NOT added to 2*eps
 
 
 def parity_tol(eps, dbl):
