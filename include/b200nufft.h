@@ -149,8 +149,17 @@ const char *const *b2n_ffi_targets(void);
 /* Message for an error code, in the wording of lib/kernels.cc.cu:54,72,78,88. */
 const char *b2n_strerror(int code);
 
-/* Drop every cached plan / workspace of the calling process (tests, memory pressure). */
+/* Drop every cached plan / workspace of the calling process and return the memory of the
+ * library's private stream-ordered pool to the driver (tests, memory pressure).  The reference
+ * holds no state between calls (it builds and destroys its plan per call, lib/kernels.cc.cu:49-51,
+ * 84); these three entry points are what a host framework uses to bound ours. */
 void b2n_cache_clear(void);
+/* Byte bound of the plan cache: after a call parks its plan, the oldest parked plans are dropped
+ * until the pool's used bytes fit.  Default: a quarter of the device (environment
+ * B2N_CACHE_BYTES); bytes < 0 restores the default.  Returns the previous limit. */
+long long b2n_set_cache_limit(long long bytes);
+/* Bytes the library's pool on the current device holds from the driver / has handed out. */
+void b2n_cache_bytes(unsigned long long *reserved, unsigned long long *used);
 
 /* Setpts cache (the reference re-sorts on every custom call,
  * lib/kernels.cc.cu:49-51,64).  When on, setpts folds the coordinate arrays into a 64-bit

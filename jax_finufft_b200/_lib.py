@@ -65,6 +65,7 @@ EXPORTED = [
     "b2n_plan_timings", "b2n_setup_spreader", "b2n_next235beven", "b2n_set_nf_type12",
     "b2n_fseries", "b2n_horner_table", "b2n_default_binsize", "b2n_version", "b2n_launch_count",
     "b2n_ffi_call", "b2n_ffi_arity", "b2n_ffi_targets", "b2n_strerror", "b2n_set_setpts_cache", "b2n_slab_partition",
+    "b2n_set_cache_limit", "b2n_cache_bytes",
 ]
 
 
@@ -109,6 +110,10 @@ def lib():
         L.b2n_strerror.argtypes = [ci]
         L.b2n_strerror.restype = C.c_char_p
         L.b2n_cache_clear.restype = None
+        L.b2n_set_cache_limit.argtypes = [C.c_longlong]
+        L.b2n_set_cache_limit.restype = C.c_longlong
+        L.b2n_cache_bytes.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+        L.b2n_cache_bytes.restype = None
         L.b2n_set_setpts_cache.argtypes = [ci]
         L.b2n_slab_partition.argtypes = [ci, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, vp, vp, vp, vp]
         L.b2n_set_setpts_cache.restype = ci

@@ -480,19 +480,30 @@ template <typename T> bool Plan<T>::can_chunk(int64_t M, int *nchunk, int64_t *c
   return *nchunk >= 2;
 }
 
+// The float tile kernels flush / gather cell PAIRS with 16-byte accesses (tile_kernels.cuh: red16,
+// float4 loads): every row and every transform's grid must start on a 16-byte boundary.  Our own
+// fine grids always do (nf even); with gpu_spreadinterponly the grid is the caller's array
+// (nf = n_modes), which may have an odd row length, an odd size per transform, or an unaligned
+// base: those run on the GM kernels (scalar 8-byte accesses) instead.
+template <typename T> static bool tile_grid_ok(const Plan<T> &p, const void *grid, int ntr) {
+  if (sizeof(T) != 4) return true;
+  return ((uintptr_t)grid & 15) == 0 && (p.nf[0] & 1) == 0 && (ntr <= 1 || (p.nftot & 1) == 0);
+}
 template <typename T>
 int Plan<T>::spread(const cpx<T> *c, const cpx<T> *prescale, cpx<T> *grid, int ntr) {
-  if constexpr (sizeof(T) == 4) {
-    if (method == 3) return spread_swr(*this, c, prescale, grid, ntr);
+  if constexpr (sizeof(T) == 4) {  // ns = 8: two cells (16 bytes) per lane
+    if (method == 3 && (ns < 8 || dim == 2 || tile_grid_ok(*this, grid, ntr))) return spread_swr(*this, c, prescale, grid, ntr);
   }
-  return method == 2 ? spread_tile<T>(*this, c, prescale, grid, ntr) : spread_gm<T>(*this, c, prescale, grid, ntr);
+  return method == 2 && tile_grid_ok(*this, grid, ntr) ? spread_tile<T>(*this, c, prescale, grid, ntr)
+                                                       : spread_gm<T>(*this, c, prescale, grid, ntr);
 }
 template <typename T>
 int Plan<T>::interp(cpx<T> *c, const cpx<T> *postscale, const cpx<T> *grid, int ntr) {
   if constexpr (sizeof(T) == 4) {
-    if (method == 3) return interp_swr(*this, c, postscale, grid, ntr);
+    if (method == 3 && (ns < 8 || dim == 2 || tile_grid_ok(*this, grid, ntr))) return interp_swr(*this, c, postscale, grid, ntr);
   }
-  return method == 2 ? interp_tile<T>(*this, c, postscale, grid, ntr) : interp_gm<T>(*this, c, postscale, grid, ntr);
+  return method == 2 && tile_grid_ok(*this, grid, ntr) ? interp_tile<T>(*this, c, postscale, grid, ntr)
+                                                       : interp_gm<T>(*this, c, postscale, grid, ntr);
 }
 
 template <typename T> static cufftResult fft_exec(cufftHandle h, cpx<T> *d, int dir) {
@@ -659,6 +670,24 @@ static std::mutex g_mu;
 static std::vector<CacheEntry> g_cache;   // free plans, oldest first
 static std::vector<CacheEntry> g_pinned;  // plans recorded into a CUDA graph (see cache_put)
 constexpr size_t CACHE_MAX = 8;
+// ... and by bytes: parked plans keep their fine grids, sort workspaces and type-3 arrays (a 3-D
+// grid with 8 stacked transforms is several GB per key), invisible to the host framework's own
+// allocator.  After a plan is parked the oldest ones are dropped until the pool's used bytes fit
+// the limit (default: a quarter of the device; B2N_CACHE_BYTES / b2n_set_cache_limit).
+static std::atomic<long long> g_cache_limit{-1};
+static size_t cache_limit_bytes() {
+  long long v = g_cache_limit.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char *e = getenv("B2N_CACHE_BYTES");
+    if (e && e[0]) v = atoll(e);
+    else {
+      size_t fr = 0, tot = 0;
+      v = cudaMemGetInfo(&fr, &tot) == cudaSuccess ? (long long)(tot / 4) : (16LL << 30);
+    }
+    g_cache_limit.store(v, std::memory_order_relaxed);
+  }
+  return (size_t)v;
+}
 
 // CUDA-graph capture.  A call made while its stream is capturing records the
 // plan's kernels, and with them the plan's buffers, into the graph: from then on the plan
@@ -738,6 +767,23 @@ static void cache_put(const CacheKey &k, PlanBase *p, cudaStream_t st, unsigned 
     cudaEventSynchronize(evict_ev);
     cudaEventDestroy(evict_ev);
     delete evict;
+  }
+  // byte bound: drop the oldest parked plans (never the one just parked) while over the limit
+  for (;;) {
+    size_t reserved = 0, used = 0;
+    pool_usage(&reserved, &used);
+    if (used <= cache_limit_bytes()) break;
+    CacheEntry old;
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      if (g_cache.size() <= 1) break;
+      old = g_cache.front();
+      g_cache.erase(g_cache.begin());
+    }
+    cudaEventSynchronize(old.done);
+    cudaEventDestroy(old.done);
+    delete old.plan;
+    cudaStreamSynchronize(st);  // the frees above are stream-ordered: make them count before re-checking
   }
 }
 
@@ -888,6 +934,21 @@ void b2n_cache_clear(void) {
   }
   if (!pinned.empty()) cudaDeviceSynchronize();  // graphs that recorded these plans must be gone by now
   for (auto &e : pinned) delete e.plan;
+  cudaDeviceSynchronize();  // the frees are stream-ordered
+  pool_trim(0);             // ... and the memory goes back to the driver
+}
+
+long long b2n_set_cache_limit(long long bytes) {
+  const long long prev = (long long)cache_limit_bytes();
+  g_cache_limit.store(bytes < 0 ? -1 : bytes, std::memory_order_relaxed);
+  return prev;
+}
+
+void b2n_cache_bytes(unsigned long long *reserved, unsigned long long *used) {
+  size_t r = 0, u = 0;
+  pool_usage(&r, &u);
+  if (reserved) *reserved = r;
+  if (used) *used = u;
 }
 
 // The body of b2n_run.  src_ready (optional): an event the stream must wait for before the first
@@ -931,6 +992,7 @@ static int run_core(int type, int dim, int is_double, cudaStream_t stream, doubl
   int warn = 0;
   if (p) {
     p->set_stream(stream);
+    warn = p->plan_warning;
   } else {
     b2n_plan h = nullptr;
     int64_t nk3[3] = {n_k ? n_k[0] : 1, n_k ? n_k[1] : 1, n_k ? n_k[2] : 1};
@@ -939,6 +1001,7 @@ static int run_core(int type, int dim, int is_double, cudaStream_t stream, doubl
     if (ier > 1) return ier;  // ret == 1 is a warning (kernels.cc.cu:52)
     warn = ier;
     p = reinterpret_cast<PlanBase *>(h);
+    p->plan_warning = warn;
   }
   int64_t n_k_total = 1;
   if (type != 3) for (int d = 0; d < dim; d++) n_k_total *= n_k[d];

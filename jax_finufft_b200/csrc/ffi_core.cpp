@@ -74,10 +74,22 @@ int b2n_ffi_call(const char *target, void *stream, const b2n_ffi_attrs *a, const
     std::fprintf(stderr, "[b200nufft] unknown custom-call target '%s'\n", target ? target : "(null)");
     return B2N_ERR_INVALID_ARGUMENT;
   }
-  if (!a || !operands || !result || n_operands != b2n_ffi_arity(target)) return B2N_ERR_INVALID_ARGUMENT;
-  for (int i = 0; i < n_operands; i++)
-    if (!operands[i]) return B2N_ERR_INVALID_ARGUMENT;
+  if (!a || !operands || n_operands != b2n_ffi_arity(target)) return B2N_ERR_INVALID_ARGUMENT;
   if (a->n_tot < 0 || a->n_j < 0 || a->n_transf < 1 || a->n_transf > 0x7fffffffLL) return B2N_ERR_NTRANS_NOTVALID;
+  // A buffer may be NULL exactly when it is empty (torch's data_ptr() of a zero-size tensor, XLA's
+  // empty buffers): nufft1 / nufft3 with n_j == 0 must return zeros, not an error.
+  {
+    int64_t n_modes = 1;
+    for (int d = 0; d < t.dim; d++) n_modes *= (d == 0 ? a->n_k_1 : d == 1 ? a->n_k_2 : a->n_k_3);
+    const int64_t n_uni = t.type == 3 ? a->n_k_1 : n_modes;            // modes, or type-3 targets
+    const int64_t n_src = t.type == 2 ? n_uni : a->n_j, n_out = t.type == 2 ? a->n_j : n_uni;
+    if (!operands[0] && a->n_tot * n_src > 0) return B2N_ERR_INVALID_ARGUMENT;
+    if (!result && a->n_tot * n_out > 0) return B2N_ERR_INVALID_ARGUMENT;
+    for (int d = 0; d < t.dim; d++) {
+      if (!operands[1 + d] && a->n_tot * a->n_j > 0) return B2N_ERR_INVALID_ARGUMENT;
+      if (t.type == 3 && !operands[1 + t.dim + d] && a->n_tot * a->n_k_1 > 0) return B2N_ERR_INVALID_ARGUMENT;
+    }
+  }
 
   // build_opts<T> of the reference (lib/kernels.cc.cu:98-113): start from the defaults, then the
   // seven attributes that cross the boundary

@@ -62,6 +62,7 @@ struct PlanBase {
   virtual void set_stream(cudaStream_t s) = 0;
   virtual cudaStream_t get_stream() const = 0;
   bool is_double = false;
+  int plan_warning = 0;  // what makeplan returned (1 = eps below machine precision): repeated on cache hits
   double timings[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -171,7 +172,9 @@ int t3_minmax(cudaStream_t st, int dim, int64_t M, const T *const *x, int64_t N,
               const T *const *s, double *lohi /* [12]: per dim lo,hi of x then of s */);
 template <typename T> int t3_prepare(Plan<T> &p, const T *const *x, const T *const *s);
 
-int dev_alloc(void **p, size_t bytes, cudaStream_t st);
+int dev_alloc(void **p, size_t bytes, cudaStream_t st);   // from the library's private pool (sort.cu)
+void pool_usage(size_t *reserved, size_t *used);
+void pool_trim(size_t keep_bytes);
 void dev_free(void *p, cudaStream_t st);
 template <typename U> inline int dev_alloc_t(U **p, size_t count, cudaStream_t st) {
   return dev_alloc((void **)p, count * sizeof(U), st);

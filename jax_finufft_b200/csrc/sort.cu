@@ -23,30 +23,66 @@
 //                     stays in L2 until its sectors are complete
 // No host readback, no stream sync.  HBM bytes per point (float, 3-D): 12 + (12+16) + (16+16)
 // = 72 B algorithmic.
+#include <mutex>
+
 #include "swr_kernels.cuh"
 
 namespace b2n {
 
-// The stream-ordered pool gives memory back to the OS at every synchronisation unless told
-// otherwise; re-mapping gigabytes per call costs far more than the transforms themselves.
-static void keep_pool_memory() {
-  static unsigned long long done = 0;  // bit per device; benign race (idempotent)
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64 || (done >> dev) & 1ull) return;
-  cudaMemPool_t mp;
-  if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+// All plan buffers come from a PRIVATE stream-ordered pool per device (not the device's default
+// pool, which other libraries in the process share): its release threshold is lifted so that
+// memory is kept across synchronisations -- re-mapping gigabytes per call costs far more than the
+// transforms themselves -- and b2n_cache_clear() / b2n_trim() hand it back explicitly.
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pool[64] = {};
+cudaMemPool_t plan_pool(int dev) {
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pool[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t mp = nullptr;
+    if (cudaMemPoolCreate(&mp, &props) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
     unsigned long long thr = ~0ull;
     cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+    g_pool[dev] = mp;
   }
-  done |= 1ull << dev;
+  return g_pool[dev];
+}
+// bytes the pool of the current device holds from the driver (reserved) and has handed out (used)
+void pool_usage(size_t *reserved, size_t *used) {
+  *reserved = *used = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pool[dev]) return;
+  unsigned long long r = 0, u = 0;
+  cudaMemPoolGetAttribute(g_pool[dev], cudaMemPoolAttrReservedMemCurrent, &r);
+  cudaMemPoolGetAttribute(g_pool[dev], cudaMemPoolAttrUsedMemCurrent, &u);
+  *reserved = (size_t)r;
+  *used = (size_t)u;
+}
+void pool_trim(size_t keep) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (g_pool[dev]) cudaMemPoolTrimTo(g_pool[dev], keep);
 }
 
 int dev_alloc(void **p, size_t bytes, cudaStream_t st) {
-  keep_pool_memory();
   if (bytes == 0) bytes = 16;
-  cudaError_t e = cudaMallocAsync(p, bytes, st);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t mp = plan_pool(dev);
+  cudaError_t e = mp ? cudaMallocFromPoolAsync(p, bytes, mp, st) : cudaMallocAsync(p, bytes, st);
   if (e != cudaSuccess) {
-    fprintf(stderr, "[b200nufft] cudaMallocAsync(%zu) failed: %s\n", bytes, cudaGetErrorString(e));
+    fprintf(stderr, "[b200nufft] device allocation of %zu bytes failed: %s\n", bytes, cudaGetErrorString(e));
     *p = nullptr;
     cudaGetLastError();
     return B2N_ERR_ALLOC;

@@ -4,10 +4,13 @@
 // 18 custom-call targets, the same typed attributes and the same operand order, so
 // src/jax_finufft/lowering.py:15-21,176-178 registers and lowers them unchanged.
 //
-// NOT built in this repository's image: it needs <xla/ffi/api/ffi.h> (shipped inside jaxlib)
-// and nanobind, neither of which is installed here.  Everything with behaviour
-// lives below the C ABI (ffi_core.cpp: b2n_ffi_call) and is exercised by tests/test_ffi_core.py;
-// this file only adapts XLA's call frame to that one function.  Build recipe: INTEGRATION.md §2.
+// NOT built into the library in this repository's image: it needs <xla/ffi/api/ffi.h> (shipped
+// inside jaxlib) and nanobind, neither of which is installed here.  Everything
+// with behaviour lives below the C ABI (ffi_core.cpp: b2n_ffi_call) and is exercised by
+// tests/test_ffi_core.py; this file only adapts XLA's call frame to that one function.
+// tests/test_xla_shim_mock.py compiles it against a mock of the xla::ffi / nanobind surface it
+// uses and runs the 18 handlers (schema, eps width, operand count, error forwarding) -- JAX
+// itself has never driven it.  Build recipe: INTEGRATION.md §2.
 //
 // Shape of the adapter: instead of one hand-written wrapper per (dim, type, precision) as
 // upstream, ONE handler template parameterised by the target index; operands arrive through
@@ -55,25 +58,26 @@ ffi::Error call(cudaStream_t stream, Eps eps, int64_t iflag, int64_t n_tot, int6
 }
 
 template <int I, typename Eps> XLA_FFI_Error *handler(XLA_FFI_CallFrame *frame) {
+  // `Eps` makes every type after .Attr<Eps> dependent: the member templates need `template`
   static auto *h = ffi::Ffi::Bind()
                        .Ctx<ffi::PlatformStream<cudaStream_t>>()
-                       .Attr<Eps>("eps")
-                       .Attr<int64_t>("iflag")
-                       .Attr<int64_t>("n_tot")
-                       .Attr<int64_t>("n_transf")
-                       .Attr<int64_t>("n_j")
-                       .Attr<int64_t>("n_k_1")
-                       .Attr<int64_t>("n_k_2")
-                       .Attr<int64_t>("n_k_3")
-                       .Attr<int64_t>("modeord")
-                       .Attr<double>("upsampfac")
-                       .Attr<int64_t>("gpu_method")
-                       .Attr<int64_t>("gpu_sort")
-                       .Attr<int64_t>("gpu_kerevalmeth")
-                       .Attr<int64_t>("gpu_maxbatchsize")
-                       .Attr<int64_t>("debug")
+                       .template Attr<Eps>("eps")
+                       .template Attr<int64_t>("iflag")
+                       .template Attr<int64_t>("n_tot")
+                       .template Attr<int64_t>("n_transf")
+                       .template Attr<int64_t>("n_j")
+                       .template Attr<int64_t>("n_k_1")
+                       .template Attr<int64_t>("n_k_2")
+                       .template Attr<int64_t>("n_k_3")
+                       .template Attr<int64_t>("modeord")
+                       .template Attr<double>("upsampfac")
+                       .template Attr<int64_t>("gpu_method")
+                       .template Attr<int64_t>("gpu_sort")
+                       .template Attr<int64_t>("gpu_kerevalmeth")
+                       .template Attr<int64_t>("gpu_maxbatchsize")
+                       .template Attr<int64_t>("debug")
                        .RemainingArgs()
-                       .Ret<ffi::AnyBuffer>()
+                       .template Ret<ffi::AnyBuffer>()
                        .To(call<I, Eps>)
                        .release();
   return h->Call(frame);

@@ -321,6 +321,29 @@ def test_spreadinterponly_matches_oracle_spread():
     assert oracle.relerr(ci[0], co) < 1e-6
 
 
+@pytest.mark.parametrize("dim,nf,ntr", [(2, (33, 20), 1), (2, (33, 21), 3), (3, (21, 16, 12), 1), (3, (15, 9, 7), 2),
+                                        (3, (34, 33, 33), 2)])
+@pytest.mark.parametrize("method", [0, 2])
+def test_spreadinterponly_odd_grids(dim, nf, ntr, method):
+    """The caller's grid with gpu_spreadinterponly has the MODE sizes: odd rows, odd sizes per
+    transform.  The float tile kernels use 16-byte cell-pair accesses, so such grids must take the
+    scalar kernels (misaligned-address faults / spills into the next row otherwise)."""
+    rng = np.random.default_rng(19)
+    M = 20000
+    pts = [rng.uniform(-np.pi, np.pi, M).astype(np.float32) for _ in range(dim)]
+    c = (rng.uniform(-1, 1, (ntr, M)) + 1j * rng.uniform(-1, 1, (ntr, M))).astype(np.complex64)
+    fw, info = run_plan(1, dim, nf, pts, [], c, 1e-5, 1, False, gpu_spreadinterponly=1, gpu_method=method)
+    p64 = [x.astype(np.float64) for x in pts]
+    for t in range(ntr):
+        fo = oracle.spread(p64, c[t], nf, info.ns, info.beta, prec=1)
+        assert oracle.relerr(fw[t], fo) < 1e-6, (dim, nf, t)
+    g = (rng.uniform(-1, 1, (ntr,) + nf[::-1]) + 1j * rng.uniform(-1, 1, (ntr,) + nf[::-1])).astype(np.complex64)
+    ci, _ = run_plan(2, dim, nf, pts, [], g, 1e-5, -1, False, gpu_spreadinterponly=1, gpu_method=method)
+    for t in range(ntr):
+        co = oracle.interp(p64, g[t], info.ns, info.beta, prec=1)
+        assert oracle.relerr(ci[t], co) < 1e-6, (dim, nf, t)
+
+
 def test_run_host_entry_point():
     """b2n_run_host: the C-ABI call a foreign-language host makes with HOST buffers."""
     from jax_finufft_b200 import _lib

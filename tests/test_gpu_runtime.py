@@ -115,3 +115,64 @@ def test_cuda_graph_capture(ndim, nm, M, cache, warm):
     finally:
         L.b2n_set_setpts_cache(prev)
         L.b2n_cache_clear()
+
+
+def test_cache_is_bounded_private_and_clearable():
+    """plan memory lives in a PRIVATE pool (the device default pool's release threshold
+    is left alone), the cache is bounded by bytes, and the package can release it."""
+    import ctypes as C
+
+    import jax_finufft_b200 as J
+    from jax_finufft_b200 import _lib
+
+    L = _lib.lib()
+    J.clear_cache()
+    thr = C.c_uint64(123)
+    cudart = C.CDLL("libcudart.so.12")
+    pool = C.c_void_p()
+    assert cudart.cudaDeviceGetDefaultMemPool(C.byref(pool), torch.cuda.current_device()) == 0
+    x = [torch.rand(200000, device="cuda") * 6 - 3 for _ in range(3)]
+    c = torch.complex(torch.rand(200000, device="cuda"), torch.rand(200000, device="cuda"))
+    J.nufft1((64, 64, 64), c, *x, eps=1e-6)
+    torch.cuda.synchronize()
+    assert cudart.cudaMemPoolGetAttribute(pool, 4, C.byref(thr)) == 0   # cudaMemPoolAttrReleaseThreshold
+    assert thr.value != 2 ** 64 - 1, "the device default pool must not be reconfigured"
+    r0, u0 = J.cache_bytes()
+    assert r0 >= u0 > 0
+    prev = J.set_cache_limit(u0 // 2)           # smaller than one parked plan: only the newest stays
+    for n in (48, 56, 72):
+        J.nufft1((n, n, n), c, *x, eps=1e-6)
+    torch.cuda.synchronize()
+    _, u1 = J.cache_bytes()
+    assert u1 < 3 * u0, (u0, u1)                # not four plans' worth
+    J.set_cache_limit(prev)
+    J.clear_cache()
+    r2, u2 = J.cache_bytes()
+    assert u2 == 0 and r2 <= r0 // 4, (r2, u2)
+
+
+def test_empty_operands_may_be_null_and_warning_repeats_on_cache_hits():
+    import jax_finufft_b200 as J
+    from jax_finufft_b200 import _lib
+    import ctypes as C
+
+    # n_j == 0: zeros out, although torch hands over NULL data pointers for the empty arrays
+    e = torch.empty(0, device="cuda")
+    f = J.nufft1((8, 6), torch.empty(0, dtype=torch.complex64, device="cuda"), e, e, eps=1e-5)
+    assert f.shape == (8, 6) and float(f.abs().max()) == 0.0
+    s = torch.rand(50, device="cuda")
+    f3 = J.nufft3(torch.empty(0, dtype=torch.complex64, device="cuda"), e, s, eps=1e-5)
+    assert f3.shape == (50,) and float(f3.abs().max()) == 0.0
+    # eps below float machine precision: warning code 1 on the first call AND on the cache hit
+    L = _lib.lib()
+    J.clear_cache()
+    a = _lib.B2nFfiAttrs()
+    a.eps, a.iflag, a.n_tot, a.n_transf, a.n_j, a.n_k_1, a.upsampfac, a.gpu_kerevalmeth, a.gpu_sort = 1e-9, 1, 1, 1, 100, 32, 2.0, 1, 1
+    x = torch.rand(100, device="cuda")
+    c = torch.complex(torch.rand(100, device="cuda"), torch.rand(100, device="cuda"))
+    out = torch.empty(32, dtype=torch.complex64, device="cuda")
+    ops = (C.c_void_p * 2)(c.data_ptr(), x.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.b2n_ffi_call(b"nufft1d1f", st, C.byref(a), ops, 2, C.c_void_p(out.data_ptr())) == 1
+    assert L.b2n_ffi_call(b"nufft1d1f", st, C.byref(a), ops, 2, C.c_void_p(out.data_ptr())) == 1
+    torch.cuda.synchronize()
