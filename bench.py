@@ -515,6 +515,30 @@ def main_ours(a):
             torch.cuda.empty_cache()
             L.b2n_cache_clear()
 
+        # ---- BASELINE config 5 sharded (ref tests/sharding_test.py:244-290): 3-D type 3,
+        # 1e7 sources split across the ranks by index range, 1e7 targets in [-64,64)^3 replicated, the
+        # partial sums all-reduced.  Strong scaling; N=1 is the plain single-GPU type 3.
+        if a.workload == "c3_t1":
+            from jax_finufft_b200 import parallel as P
+            try:
+                g5 = torch.Generator(device=dev).manual_seed(4)
+                M5 = 10 ** 7
+                x5 = [(torch.rand(M5, device=dev, generator=g5) * 2 - 1) * np.pi for _ in range(3)]
+                s5 = [(torch.rand(M5, device=dev, generator=g5) * 2 - 1) * 64.0 for _ in range(3)]
+                c5 = make_complex((M5,), dev, g5)
+                lo, hi = P.shard_range(M5, world, rank)
+                xl, cl = [t[lo:hi].contiguous() for t in x5], c5[lo:hi].contiguous()
+                fn = lambda: P.nufft3_sharded_sources(cl, *xl, *s5, eps=1e-6, iflag=-1)
+                ms5, _ = timed(fn, 3, 2)
+                also["c5_t3_sources_sharded"] = {"value": M5 / (ms5 * 1e-3), "unit": UNIT, "ms_per_step": ms5, "steps": 3,
+                                                 "scaling": "strong", "M_sources": M5, "N_targets": M5, "eps": 1e-6,
+                                                 "targets": "[-64,64)^3 replicated", "collective": "all_reduce of the 1e7 targets (80 MB)"}
+                del x5, s5, c5, xl, cl, fn
+            except Exception as ex:  # noqa: BLE001
+                also["c5_t3_sources_sharded"] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+            torch.cuda.empty_cache()
+            L.b2n_cache_clear()
+
         # ---- the kernel to beat: the UNMODIFIED reference cuFINUFFT (oracle/_ref, built from
         # /root/reference by oracle/Makefile.ref) on the same B200 and the same tensors, timed the way
         # V/perftest/cuda/cuperftest.cu:183-303 does (CUDA events; setpts + execute with the plan kept)

@@ -336,12 +336,12 @@ def test_spreadinterponly_odd_grids(dim, nf, ntr, method):
     p64 = [x.astype(np.float64) for x in pts]
     for t in range(ntr):
         fo = oracle.spread(p64, c[t], nf, info.ns, info.beta, prec=1)
-        assert oracle.relerr(fw[t], fo) < 1e-6, (dim, nf, t)
+        assert oracle.relerr(fw[t], fo) < 3e-6, (dim, nf, t)   # up to 20 points per cell: fp32 summation order
     g = (rng.uniform(-1, 1, (ntr,) + nf[::-1]) + 1j * rng.uniform(-1, 1, (ntr,) + nf[::-1])).astype(np.complex64)
     ci, _ = run_plan(2, dim, nf, pts, [], g, 1e-5, -1, False, gpu_spreadinterponly=1, gpu_method=method)
     for t in range(ntr):
         co = oracle.interp(p64, g[t], info.ns, info.beta, prec=1)
-        assert oracle.relerr(ci[t], co) < 1e-6, (dim, nf, t)
+        assert oracle.relerr(ci[t], co) < 3e-6, (dim, nf, t)
 
 
 def test_run_host_entry_point():
