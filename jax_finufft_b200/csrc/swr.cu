@@ -53,8 +53,14 @@ template <int NS> struct SwrDispatch {
 #if SWR_GEN == 2
       using C = Swr2Cfg<NS>;
       dim3 grid((unsigned)p.pts.sp_cap, (unsigned)ntr);
-      B2N_CUDA_OK(cudaFuncSetAttribute(k_swr2_spread<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SPREAD_SMEM));
-      k_swr2_spread<NS><<<grid, 32, C::SPREAD_SMEM, p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
+      if (a.scale) {  // type 3: strengths times the prephase
+        B2N_CUDA_OK(cudaFuncSetAttribute(k_swr2_spread<NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SPREAD_SMEM));
+        k_swr2_spread<NS, true><<<grid, 32, C::SPREAD_SMEM, p.stream>>>(a, p.tab);
+      } else {
+        B2N_CUDA_OK(cudaFuncSetAttribute(k_swr2_spread<NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SPREAD_SMEM));
+        k_swr2_spread<NS, false><<<grid, 32, C::SPREAD_SMEM, p.stream>>>(a, p.tab);
+      }
+      B2N_LAUNCHED(1);
 #else
       using C = SwrCfg<NS>;
       dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);

@@ -58,10 +58,18 @@ template <int NS> struct Swr2Cfg : SwrCfg<NS> {
   static constexpr int ROW0 = KZO + KZW;
   static constexpr int ROW = (ROW0 / 4) % 2 == 1 ? ROW0 : ROW0 + 4;  // stride/4 odd (see SwrCfg)
   static constexpr int NV = KZW / 4;
+  // CTAs per SM of the spreader.  With the look-ahead in shared memory the ns = 6, 7 kernels fit 96
+  // registers without spills: 18 per SM (C3: 6.81 ms; 16 -> 7.11, 20 -> 6.97)
+#ifdef SWR2_MINB
+  static constexpr int MINB2 = SWR2_MINB;
+#else
+  static constexpr int MINB2 = (NS == 6 || NS == 7) ? 18 : B::MINB;
+#endif
   static constexpr int NROWS = B::PB + 1;       // + one row: the rolling loads of the last point read a row ahead
   static constexpr int ZBIAS = 16 * B::D;       // planes are counted from zb = z0 - H - ZBIAS: always > 0
   static constexpr int SPREAD_FLOATS = NROWS * ROW;
-  static constexpr int SPREAD_SMEM = SPREAD_FLOATS * (int)sizeof(float);
+  // spread: rows + the look-ahead rings (3 x 32 records of 16 B, 2 x 32 strengths of 8 B)
+  static constexpr int SPREAD_SMEM = (SPREAD_FLOATS + 3 * 128 + 2 * 64) * (int)sizeof(float);
   // interp: rows + RES[16][33] float2 + the staging ring [STG][S][32] of float2 (x CX)
   static constexpr int RES_OFF = SPREAD_FLOATS;
   static constexpr int STG_OFF = RES_OFF + 2 * 16 * 33;  // 1056 floats: stays 16-byte aligned
@@ -108,6 +116,17 @@ __device__ __forceinline__ int lds32(unsigned a) {
   int v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
+}
+
+__device__ __forceinline__ void cp_async8_u32(unsigned d, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_u32(unsigned d, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // the three kernel vectors of one point in one Horner sweep, two intervals per FFMA2; NC > 0:
@@ -243,8 +262,8 @@ template <int NS> struct Swr2Row {
 };
 
 // ==================================================================================== SPREAD
-template <int NS>
-__global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
+template <int NS, bool SCALED>
+__global__ void __launch_bounds__(32, Swr2Cfg<NS>::MINB2)
     k_swr2_spread(const SwrArgs a, const __grid_constant__ HornerTable<float> tab) {
   using C = Swr2Cfg<NS>;
   constexpr int D = C::D, S = C::S, CX = C::CX, NV = C::NV;
@@ -259,11 +278,6 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
   const int xa = x0 - C::H, ya = y0 - C::H, zb = z0 - C::H - C::ZBIAS;
   const int nf0 = a.nf[0], nf1 = a.nf[1], nf2 = a.nf[2];
   const int64_t pstride = (int64_t)nf0 * nf1;
-  float2 *cell[S];  // this lane's cell of each row slot in plane 0
-#pragma unroll
-  for (int s = 0; s < S; s++)
-    cell[s] = a.fw + (int64_t)blockIdx.y * a.nftot +
-              (wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0));
 
   float2 acc[S][CX][D];
 #pragma unroll
@@ -283,9 +297,9 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
     gz = prel + zb;
     gz = gz < 0 ? gz + nf2 : gz;
     if (gz >= nf2) gz = gz - nf2 < nf2 ? gz - nf2 : gz % nf2;
-    const int64_t po = (int64_t)gz * pstride;
+    float2 *base = a.fw + (int64_t)blockIdx.y * a.nftot + (int64_t)gz * pstride + wrap_once(xa + CX * q, nf0);
 #pragma unroll
-    for (int s = 0; s < S; s++) pz[s] = cell[s] + po;
+    for (int s = 0; s < S; s++) pz[s] = base + wrap_once(ya + 4 * s + r, nf1) * nf0;  // once per subproblem (or gap)
   };
   auto retire = [&](int slot) {
     auto one = [&](auto kc) {
@@ -361,24 +375,35 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
 
   int cur = SWR_EMPTY;  // first (relative) plane held by the ring
   int slot = 0;         // ring slot of plane cur = cur mod D
-  // Two-deep software pipeline over batches of 32 points (see k_swr_spread)
+  // Two-deep pipeline over batches of 32 points, entirely in shared memory (cp.async): the record
+  // of batch b+2 and the strength of batch b+1 (whose address comes from the record of b+1) are in
+  // flight while the warp spreads batch b.  (Held in registers, as in the first generation, the
+  // look-ahead costs 14 registers -- and when the register budget is tightened ptxas spills exactly
+  // those, right behind their loads: every batch then waits out a DRAM round trip, profiles/r02h.)
   const PtRec<float> *recp = a.rec + first + lane;
-  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto ldc = [&](const float4 &rc, float2 &sc) {
-    const int o = __float_as_int(rc.w);
-    if (a.scale) sc = __ldg(a.scale + o);
-    return ld_stream2(cin + o);
+  const unsigned rq = sm0 + (C::SPREAD_FLOATS + 4 * lane) * 4;        // record ring: 3 slots x 32 x 16 B
+  const unsigned cq = sm0 + (C::SPREAD_FLOATS + 3 * 128 + 2 * lane) * 4;  // strength ring: 2 slots x 32 x 8 B
+  auto issue_rec = [&](int b) {  // batch index b -> slot b % 3
+    if (b * C::PB + lane < cnt) cp_async16_u32(rq + (b % 3) * 512, recp + b * C::PB);
+    cp_async_commit();
   };
-  const float2 zero2 = make_float2(0.f, 0.f);
-  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
-  float4 recB = lane + C::PB < cnt ? ld_stream4(recp + C::PB) : zrec;
-  float2 sA = make_float2(1.f, 0.f), sB = sA;
-  float2 cA = lane < cnt ? ldc(recA, sA) : zero2;
+  auto issue_str = [&](int b) {  // needs the record of batch b in shared memory
+    if (b * C::PB + lane < cnt) cp_async8_u32(cq + (b & 1) * 256, cin + lds32(rq + (b % 3) * 512 + 12));
+    cp_async_commit();
+  };
+  issue_rec(0);
+  issue_rec(1);
+  cp_async_wait<1>();
+  issue_str(0);
   sentinel(C::PB);
-  for (int b0 = 0; b0 < cnt; b0 += C::PB) {
+  int bi = 0;
+  for (int b0 = 0; b0 < cnt; b0 += C::PB, bi++) {
     const int nb = min(C::PB, cnt - b0);
-    const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
-    const float2 cB = b0 + C::PB + lane < cnt ? ldc(recB, sB) : zero2;
+    issue_rec(bi + 2);
+    cp_async_wait<1>();   // record bi+1 and strength bi have landed
+    issue_str(bi + 1);
+    const float4 recA = lane < nb ? lds128(rq + (bi % 3) * 512) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 cA = lane < nb ? lds64(cq + (bi & 1) * 256) : make_float2(0.f, 0.f);
     __syncwarp();
     int pos, cls;
 #if SWR_YCLASS
@@ -387,16 +412,14 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
     pos = lane; cls = 1;
 #endif
     if (lane < nb) {
-      float2 cv = cA;
-      if (a.scale) cv = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
-      swr2_weights<NS>(tab, recA, cv, xa, ya, zb, rows + pos * C::ROW, 0, cls);
+      if constexpr (SCALED) {  // type 3: strength times the prephase of the point
+        const float2 sA = __ldg(a.scale + __float_as_int(recA.w));
+        cA = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
+      }
+      swr2_weights<NS>(tab, recA, cA, xa, ya, zb, rows + pos * C::ROW, 0, cls);
     }
     if (nb < C::PB) sentinel(nb);
     __syncwarp();
-    recA = recB;
-    recB = recC;
-    cA = cB;
-    sA = sB;
     ax = ax0; ay = ay0; az = az0;
     pr.load_all(ax, ay, az);
     for (;;) {
@@ -441,6 +464,7 @@ __global__ void __launch_bounds__(32, SwrCfg<NS>::MINB)
       retire(slot);
       slot = slot + 1 == D ? 0 : slot + 1;
     }
+  cp_async_wait<0>();
 }
 
 }  // namespace b2n
