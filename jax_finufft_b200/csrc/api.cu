@@ -104,6 +104,7 @@ template <typename T> Plan<T>::~Plan() {
     dev_free(sp[d], st);
   }
   dev_free(fw, st);
+  dev_free(cpack, st);
   dev_free(pts.rec, st);
   dev_free(pts.tmp, st);
   dev_free(pts.idx, st);
@@ -303,9 +304,12 @@ template <typename T> void Plan<T>::set_geometry(int64_t M) {
   bool swr = swr_ok && nf[0] % 2 == 0 && nf[0] >= 32 && nf[1] >= 32 &&
              (dim == 3 ? nf[2] >= 32 && (double)M >= dens3 * (double)nftot : (double)M >= dens2 * (double)nftot);
   if (force && swr_ok) swr = force[0] == '3';
+  // 2-D type 1 with stacked transforms (jax-finufft's vmap stacking, BASELINE config 4): the
+  // narrow-window stacked spreader and its bins
+  stacked2 = swr && sizeof(T) == 4 && dim == 2 && type == 1 && batch >= 2 && ns <= 7 && !opts.gpu_spreadinterponly;
   if (swr) {
     method = 3;
-    swr_bins(dim, ns, bin);
+    swr_bins(dim, ns, bin, stacked2);
     maxsub = opts.gpu_maxsubprobsize > 0 ? opts.gpu_maxsubprobsize : 2048;
   } else {
     method = base_method;

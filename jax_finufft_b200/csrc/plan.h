@@ -86,6 +86,9 @@ template <typename T> struct Plan : PlanBase {
   // register kernels may take over once the point count is known (set_geometry, at setpts)
   int base_method = 0, base_bin[3] = {1, 1, 1}, base_maxsub = 1024;
   bool swr_ok = false;
+  bool stacked2 = false;  // 2-D type 1 with stacked transforms: narrow-window bins (rt2_kernels.cuh, Rt2sCfg)
+  cpx<T> *cpack = nullptr;  // point-major strengths of one batch of transforms [M][8]
+  int64_t cap_cpack = 0;
   HornerTable<T> tab;
   cudaStream_t stream = 0;
 
@@ -154,7 +157,7 @@ template <typename T>
 int interp_gm(Plan<T> &p, cpx<T> *c, const cpx<T> *postscale, const cpx<T> *fw, int ntr);
 
 // register kernels (swr.cu): sliding window (3-D) / register tile (2-D), float, ns <= 8, bins from swr_bins()
-void swr_bins(int dim, int ns, int *bin);
+void swr_bins(int dim, int ns, int *bin, bool stacked2 = false);
 int spread_swr(Plan<float> &p, const float2 *c, const float2 *prescale, float2 *fw, int ntr);
 int interp_swr(Plan<float> &p, float2 *c, const float2 *postscale, const float2 *fw, int ntr);
 

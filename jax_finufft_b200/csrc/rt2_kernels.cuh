@@ -366,6 +366,186 @@ __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)
   }
 }
 
+// ==================================================================================== SPREAD, stacked, narrow window
+// Second generation of the stacked spreader (BASELINE config 4: 64 transforms sharing 1e7 points).
+// k_rt2_spread_nt above inherits the 16 x 16 window of the single-transform kernel: 49 of its 256
+// cells lie in a point's stencil, so per point and transform it issues 2 FMUL2 + 8 FFMA2 of which
+// 19 % are useful, and it gathers every strength on its own (one 128-byte line per 8 bytes).  Here:
+//   * the window is the 8 x 12 one of the 3-D kernels (bins of 2 x 6 anchor cells at ns = 7): lane
+//     (r, q) owns x cell q of rows {r, r+4, r+8}; per point and transform 1 FMUL2 + 3 FFMA2;
+//   * NT = 8 transforms per pass (24 complex accumulators per lane), so the kernel vectors are
+//     evaluated and loaded once per 8 transforms;
+//   * the strengths are first re-laid out POINT-major, [M][8] (k_pack_strengths: one coalesced
+//     pass over the batch), so the gather through idx brings 64 useful bytes per point and pass,
+//     and it is made by cp.async straight into shared memory, one batch ahead.
+#ifndef RT2S_S
+#define RT2S_S 3
+#endif
+#ifndef RT2S_NT
+#define RT2S_NT 8
+#endif
+template <int NS> struct Rt2sCfg {
+  static constexpr int NT = RT2S_NT;
+  static constexpr int S = RT2S_S;
+  static constexpr int WX = 8, WY = 4 * S;
+  static constexpr int H = NS / 2;
+  static constexpr int BX = WX - NS + 1, BY = WY - NS + 1;
+  static constexpr int PB = 32;
+  static constexpr int NP = (NS + 1) / 2;
+  static constexpr int KXO = 0;        // 8 x weights (zero outside the stencil)
+  static constexpr int KYO = 8;        // ky[r = row & 3][row >> 2], 4 x 4 (3 used)
+  static constexpr int ROW = 28;       // 24 floats + 4: stride / 4 odd
+  static constexpr int CSO = PB * ROW; // strengths: [2 buffers][PB points][NT complex]
+  static constexpr int SMEM = (CSO + 2 * PB * 2 * NT) * (int)sizeof(float);
+  static_assert(BX >= 1 && BY >= 1, "window too small");
+};
+
+// cpack[i][t] = c[t][i], t < NT (zero beyond nt): a tiled transpose is not needed -- every thread
+// writes the 64 contiguous bytes of its point, a warp 2 KB
+template <int NT>
+__global__ void __launch_bounds__(256) k_pack_strengths(const float2 *__restrict__ c, int64_t M, int nt,
+                                                         float2 *__restrict__ cpack) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float2 v[NT];
+#pragma unroll
+  for (int t = 0; t < NT; t++) v[t] = t < nt ? __ldcs(c + (int64_t)t * M + i) : make_float2(0.f, 0.f);
+  float4 *dst = reinterpret_cast<float4 *>(cpack + i * NT);
+#pragma unroll
+  for (int t = 0; t < NT; t += 2) dst[t / 2] = make_float4(v[t].x, v[t].y, v[t + 1].x, v[t + 1].y);
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __grid_constant__ HornerTable<float> tab,
+                                                     const float2 *__restrict__ cpack, int nt) {
+  using C = Rt2sCfg<NS>;
+  constexpr int S = C::S, NP = C::NP, NT = C::NT;
+  extern __shared__ __align__(16) float swr_smem[];
+  const int lane = threadIdx.x;
+  int first, cnt, x0, y0;
+  if (!swr_decode(a, blockIdx.x, first, cnt, x0, y0)) return;
+  float *rows = swr_smem;
+  const unsigned sm0 = (unsigned)__cvta_generic_to_shared(swr_smem);
+  const int r = lane >> 3, q = lane & 7;
+  const int xa = x0 - C::H, ya = y0 - C::H;
+  const int nf0 = a.nf[0], nf1 = a.nf[1];
+
+  float2 acc[NT][S];
+#pragma unroll
+  for (int t = 0; t < NT; t++)
+#pragma unroll
+    for (int s = 0; s < S; s++) acc[t][s] = make_float2(0.f, 0.f);
+
+  const PtRec<float> *recp = a.rec + first + lane;
+  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the 64 bytes of strengths of the point of record rc -> buffer `buf`, row `lane`
+  auto issue_str = [&](int buf, const float4 &rc, bool valid) {
+    if (valid) {
+      const float2 *src = cpack + (int64_t)__float_as_int(rc.w) * NT;
+      const unsigned dst = sm0 + (C::CSO + (buf * C::PB + lane) * 2 * NT) * 4;
+#pragma unroll
+      for (int k = 0; k < NT / 2; k++)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * k), "l"(src + 2 * k) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
+  float4 recB = lane + C::PB < cnt ? ld_stream4(recp + C::PB) : zrec;
+  issue_str(0, recA, lane < cnt);
+  const unsigned ax = sm0 + (C::KXO + q) * 4, ay = sm0 + (C::KYO + 4 * r) * 4;
+  int bi = 0;
+  for (int b0 = 0; b0 < cnt; b0 += C::PB, bi++) {
+    const int nb = min(C::PB, cnt - b0);
+    const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
+    issue_str((bi + 1) & 1, recB, b0 + C::PB + lane < cnt);
+    __syncwarp();
+    if (lane < nb) {  // kernel vectors of point b0 + lane, once for all transforms
+      float *row = rows + lane * C::ROW;
+      const float px = recA.x, py = recA.y;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 6; i++) reinterpret_cast<float4 *>(row)[i] = z4;
+      const int isx = window_start(px, NS), isy = window_start(py, NS);
+      float kx[2 * NP], ky[2 * NP];
+      if (!tab.direct) {
+        const float zx = fmaf(2.f, float(isx) - px, float(NS - 1));
+        const float zy = fmaf(2.f, float(isy) - py, float(NS - 1));
+        const float2 zx2 = make_float2(zx, zx), zy2 = make_float2(zy, zy);
+        float2 ax2[NP], ay2[NP];
+#pragma unroll
+        for (int j = 0; j < NP; j++) ax2[j] = ay2[j] = make_float2(tab.c[0][2 * j], tab.c[0][2 * j + 1]);
+        for (int k = 1; k < tab.ncoef; k++) {
+#pragma unroll
+          for (int j = 0; j < NP; j++) {
+            const float2 cj = make_float2(tab.c[k][2 * j], tab.c[k][2 * j + 1]);
+            ax2[j] = fma2(ax2[j], zx2, cj);
+            ay2[j] = fma2(ay2[j], zy2, cj);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+          kx[2 * j] = ax2[j].x; kx[2 * j + 1] = ax2[j].y;
+          ky[2 * j] = ay2[j].x; ky[2 * j + 1] = ay2[j].y;
+        }
+      } else {
+        float tx[NS], ty[NS];
+        eval_kernel<float, NS>(tx, float(isx) - px, tab);
+        eval_kernel<float, NS>(ty, float(isy) - py, tab);
+#pragma unroll
+        for (int j = 0; j < NS; j++) { kx[j] = tx[j]; ky[j] = ty[j]; }
+      }
+      int xl = isx - xa;
+      xl = xl < 0 ? 0 : (xl > C::WX - NS ? C::WX - NS : xl);
+      int yl = isy - ya;
+      yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
+#pragma unroll
+      for (int j = 0; j < NS; j++) {
+        row[C::KXO + xl + j] = kx[j];
+        const int iy = yl + j;
+        row[C::KYO + 4 * (iy & 3) + (iy >> 2)] = ky[j];
+      }
+    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's strengths have landed
+    __syncwarp();
+    recA = recB;
+    recB = recC;
+    const unsigned cs = sm0 + (C::CSO + (bi & 1) * C::PB * 2 * NT) * 4;
+#pragma unroll 2
+    for (int p = 0; p < nb; p++) {
+      float kxv;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(kxv) : "r"(ax + p * C::ROW * 4));
+      float4 ky4;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ky4.x), "=f"(ky4.y), "=f"(ky4.z), "=f"(ky4.w) : "r"(ay + p * C::ROW * 4));
+      const float2 kx2 = make_float2(kxv, kxv);
+      const float2 kys[4] = {make_float2(ky4.x, ky4.x), make_float2(ky4.y, ky4.y), make_float2(ky4.z, ky4.z), make_float2(ky4.w, ky4.w)};
+#pragma unroll
+      for (int t = 0; t < NT; t += 2) {
+        float4 c2;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c2.x), "=f"(c2.y), "=f"(c2.z), "=f"(c2.w) : "r"(cs + (p * 2 * NT + 2 * t) * 4));
+        const float2 w0 = mul2(make_float2(c2.x, c2.y), kx2), w1 = mul2(make_float2(c2.z, c2.w), kx2);
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+          acc[t][s] = fma2(w0, kys[s], acc[t][s]);
+          acc[t + 1][s] = fma2(w1, kys[s], acc[t + 1][s]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const int gx = wrap_once(xa + q, nf0);
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    if (t >= nt) break;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      const int gy = wrap_once(ya + 4 * s + r, nf1);
+      if (acc[t][s].x != 0.f || acc[t][s].y != 0.f)
+        red_add(a.fw + (int64_t)t * a.nftot + (int64_t)gy * nf0 + gx, acc[t][s]);
+    }
+  }
+}
+
 // ==================================================================================== INTERP
 template <int NS>
 __global__ void __launch_bounds__(32 * Rt2Cfg<NS>::WARPS)

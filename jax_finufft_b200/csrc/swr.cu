@@ -1,4 +1,6 @@
 // swr.cu -- ns dispatch + launch of the sliding-window register kernels (3-D, float, ns <= 8).
+#include <algorithm>
+
 #include "rt2_kernels.cuh"
 #include "swr2_kernels.cuh"
 
@@ -22,9 +24,10 @@ template <int NS> static void swr_bins_ns(int ns, int *bin) {
 }
 // bins (in anchor cells) of the register kernels for kernel width ns: sliding window (3-D) or
 // register tile (2-D, Rt2Cfg: (17 - ns)^2)
-void swr_bins(int dim, int ns, int *bin) {
+void swr_bins(int dim, int ns, int *bin, bool stacked2) {
   if (dim == 2) {
-    bin[0] = bin[1] = 17 - ns;
+    bin[0] = stacked2 ? 9 - ns : 17 - ns;   // Rt2sCfg (8 x 12 window) : Rt2Cfg (16 x 16)
+    bin[1] = stacked2 ? 4 * RT2S_S + 1 - ns : 17 - ns;
     bin[2] = 1;
     return;
   }
@@ -137,6 +140,33 @@ template <> struct Rt2Dispatch<9> {
   static int interp(Plan<float> &, const SwrArgs &, int) { return B2N_ERR_METHOD_NOTVALID; }
 };
 
+template <int NS> static int rt2s_spread(Plan<float> &p, const SwrArgs &a, const float2 *c, int ntr) {
+  if (p.ns == NS) {
+    using C = Rt2sCfg<NS>;
+    const int64_t M = p.pts.M;
+    if (M > p.cap_cpack) {
+      dev_free(p.cpack, p.stream);
+      p.cpack = nullptr;
+      p.cap_cpack = 0;
+      if (int e = dev_alloc_t(&p.cpack, (size_t)M * C::NT, p.stream)) return e;
+      p.cap_cpack = M;
+    }
+    B2N_CUDA_OK(cudaFuncSetAttribute(k_rt2s_spread<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    for (int t0 = 0; t0 < ntr; t0 += C::NT) {  // ntr <= batch <= 8 by default: one pass
+      const int nt = std::min(C::NT, ntr - t0);
+      SwrArgs b = a;
+      b.fw = a.fw + (int64_t)t0 * a.nftot;
+      k_pack_strengths<C::NT><<<cdiv(M, 256), 256, 0, p.stream>>>(c + (int64_t)t0 * M, M, nt, p.cpack);
+      k_rt2s_spread<NS><<<(unsigned)p.pts.sp_cap, 32, C::SMEM, p.stream>>>(b, p.tab, p.cpack, nt);
+      B2N_LAUNCHED(2);
+    }
+    B2N_LAUNCH_OK();
+    return 0;
+  }
+  if constexpr (NS < 7) return rt2s_spread<NS + 1>(p, a, c, ntr);
+  return B2N_ERR_METHOD_NOTVALID;
+}
+
 int spread_swr(Plan<float> &p, const float2 *c, const float2 *prescale, float2 *fw, int ntr) {
   if (p.pts.M == 0 || p.pts.sp_cap == 0) return 0;
   SwrArgs a;
@@ -145,6 +175,7 @@ int spread_swr(Plan<float> &p, const float2 *c, const float2 *prescale, float2 *
   a.cout = nullptr;
   a.scale = prescale;
   a.fw = fw;
+  if (p.dim == 2 && p.stacked2) return rt2s_spread<2>(p, a, c, ntr);  // the bins are the narrow-window ones
   if (p.dim == 2) return Rt2Dispatch<2>::spread(p, a, ntr);
   return SwrDispatch<2>::spread(p, a, ntr);
 }
