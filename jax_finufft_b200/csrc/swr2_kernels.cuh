@@ -343,16 +343,21 @@ __global__ void __launch_bounds__(32, Swr2Cfg<NS>::MINB2)
   // all ns^2 x ns cell updates of the point held in `pr`, then roll `pr` on to the next row.
   // CLS: 0 = the point's y window ends below row slot S-1, 2 = it starts above row slot 0,
   // 1 = anything: the untouched slot's FMUL2 + D FFMA2 are not issued at all
-  auto point = [&](auto clc) {
+  // The rolling loads address the row K rows ahead of (ax, ay, az) with an immediate offset; the
+  // pointers move once per two points (advance), far from the loads that use them -- bumped right
+  // behind an LDS, the add waits for the load to release its address register (short-scoreboard
+  // stalls on every pointer increment, profiles/r02k source view).
+  auto advance = [&](int k) { ax += k * RB; ay += k * RB; az += k * RB; };
+  auto point = [&](auto clc, auto kc) {
     constexpr int CLS = decltype(clc)::value;
+    constexpr unsigned K = decltype(kc)::value;
     constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
     float2 wv[S][CX];
 #pragma unroll
     for (int s = S0; s < S1; s++)
 #pragma unroll
       for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
-    ax += RB; ay += RB; az += RB;
-    pr.load_xy(ax, ay);
+    pr.load_xy(ax + K * RB, ay + K * RB);
 #pragma unroll
     for (int i = 0; i < NV; i++) {
 #pragma unroll
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(32, Swr2Cfg<NS>::MINB2)
             for (int c = 0; c < CX; c++) acc[s][c][j] = fma2(wv[s][c], kzj, acc[s][c][j]);
         }
       }
-      pr.load_kv(az, i);
+      pr.load_kv(az + K * RB, i);
     }
   };
   const unsigned sm0 = smem_u32(swr_smem);
@@ -444,18 +449,22 @@ __global__ void __launch_bounds__(32, Swr2Cfg<NS>::MINB2)
         }
       }
       const int k0 = mt & ~3;
-      while (mt == k0) {
-        point(std::integral_constant<int, 0>{});
-        mt = pr.meta();
+#define SWR2_RUN(CL)                                                                            \
+      while (mt == k0 + CL) { /* two points per trip; (ax, ay, az) = the row held in pr */       \
+        point(std::integral_constant<int, CL>{}, std::integral_constant<unsigned, 1>{});         \
+        mt = pr.meta();                                                                          \
+        if (mt != k0 + CL) {                                                                     \
+          advance(1);                                                                            \
+          break;                                                                                 \
+        }                                                                                        \
+        point(std::integral_constant<int, CL>{}, std::integral_constant<unsigned, 2>{});         \
+        advance(2);                                                                              \
+        mt = pr.meta();                                                                          \
       }
-      while (mt == k0 + 1) {
-        point(std::integral_constant<int, 1>{});
-        mt = pr.meta();
-      }
-      while (mt == k0 + 2) {
-        point(std::integral_constant<int, 2>{});
-        mt = pr.meta();
-      }
+      SWR2_RUN(0)
+      SWR2_RUN(1)
+      SWR2_RUN(2)
+#undef SWR2_RUN
     }
   }
   if (cur != SWR_EMPTY)
