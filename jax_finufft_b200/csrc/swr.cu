@@ -4,12 +4,9 @@
 #include "rt2_kernels.cuh"
 #include "swr2_kernels.cuh"
 
-// 3-D spreader: 2 = k_swr2_spread (swr2_kernels.cuh: absolute ring slots), 1 = the phase-chain
-// k_swr_spread of swr_kernels.cuh (A/B builds: make EXTRA=-DSWR_GEN=1).  Interpolation always runs
-// the phase-chain k_swr_interp (an absolute-slot version was slower: DESIGN.md 4.3).
-#ifndef SWR_GEN
-#define SWR_GEN 2
-#endif
+// 3-D: spreader k_swr2_spread (swr2_kernels.cuh: absolute ring slots), interpolator k_swr_interp
+// (swr_kernels.cuh: phase chain + cp.async plane staging; an absolute-slot version was slower,
+// DESIGN.md 4.3).
 
 namespace b2n {
 
@@ -53,7 +50,6 @@ static void swr_fill(Plan<float> &p, SwrArgs &a) {
 template <int NS> struct SwrDispatch {
   static int spread(Plan<float> &p, const SwrArgs &a, int ntr) {
     if (p.ns == NS) {
-#if SWR_GEN == 2
       using C = Swr2Cfg<NS>;
       dim3 grid((unsigned)p.pts.sp_cap, (unsigned)ntr);
       if (a.scale) {  // type 3: strengths times the prephase
@@ -64,12 +60,6 @@ template <int NS> struct SwrDispatch {
         k_swr2_spread<NS, false><<<grid, 32, C::SPREAD_SMEM, p.stream>>>(a, p.tab);
       }
       B2N_LAUNCHED(1);
-#else
-      using C = SwrCfg<NS>;
-      dim3 grid((unsigned)cdiv(p.pts.sp_cap, C::WARPS), (unsigned)ntr);
-      B2N_CUDA_OK(cudaFuncSetAttribute(k_swr_spread<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bytes()));
-      k_swr_spread<NS><<<grid, 32 * C::WARPS, C::smem_bytes(), p.stream>>>(a, p.tab);  B2N_LAUNCHED(1);
-#endif
       B2N_LAUNCH_OK();
       return 0;
     }

@@ -1,4 +1,7 @@
-// swr_kernels.cuh -- sliding-window REGISTER spreading / interpolation, 3-D, float, ns <= 8.
+// swr_kernels.cuh -- sliding-window REGISTER kernels, 3-D, float, ns <= 8: the shared geometry
+// (SwrCfg, anchors, batch ordering) and the INTERPOLATOR k_swr_interp; the spreader is
+// k_swr2_spread (swr2_kernels.cuh).  The description below covers both; the spreader's phase-chain
+// first generation (k_swr_spread, round 1: 7.34 ms at C3) was replaced in round 2.
 // Replaces spread_3d_subprob / spread_3d_output_driven and interp_3d_nupts_driven / interp_3d_subprob
 // (V/src/cuda/3d/spreadinterp3d.cuh:138-383, 556-712) on the headline path (3-D c64, eps >= 1e-7).
 //
@@ -299,212 +302,6 @@ template <int NS> struct SwrRow {
     return make_float2(k, k);
   }
 };
-
-// ==================================================================================== SPREAD
-template <int NS>
-__global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
-    k_swr_spread(const SwrArgs a, const __grid_constant__ HornerTable<float> tab) {
-  using C = SwrCfg<NS>;
-  constexpr int D = C::D, S = C::S, CX = C::CX;
-  extern __shared__ __align__(16) float swr_smem[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int first, cnt, x0, y0;
-  if (!swr_decode(a, blockIdx.x * C::WARPS + w, first, cnt, x0, y0)) return;
-  float *rows = swr_smem + w * (C::PB * C::ROW);
-  const float2 *cin = a.cin + (int64_t)blockIdx.y * a.M;
-
-  const int r = lane >> 3, q = lane & 7;
-  const int xa = x0 - C::H, ya = y0 - C::H;
-  const int nf0 = a.nf[0], nf1 = a.nf[1], nf2 = a.nf[2];
-  const int64_t pstride = (int64_t)nf0 * nf1;
-  // this lane's cell of each row slot in plane 0
-  float2 *cell[S];
-#pragma unroll
-  for (int s = 0; s < S; s++)
-    cell[s] = a.fw + (int64_t)blockIdx.y * a.nftot +
-              (wrap_once(ya + 4 * s + r, nf1) * nf0 + wrap_once(xa + CX * q, nf0));
-
-  float2 acc[S][CX][D];
-#pragma unroll
-  for (int s = 0; s < S; s++)
-#pragma unroll
-    for (int c = 0; c < CX; c++)
-#pragma unroll
-      for (int k = 0; k < D; k++) acc[s][c][k] = make_float2(0.f, 0.f);
-
-  // retire plane p held by ring slot K (a literal): RED this lane's cells, clear the slot
-  auto retire = [&](auto kc, int p) {
-    constexpr int K = decltype(kc)::value;
-    const int gz = p < 0 ? p + nf2 : (p >= nf2 ? p - nf2 : p);
-    const int64_t po = (int64_t)gz * pstride;
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      if constexpr (CX == 1) {
-        red_add(cell[s] + po, acc[s][0][K]);
-      } else {
-        red_add4(reinterpret_cast<float4 *>(cell[s] + po),
-                 make_float4(acc[s][0][K].x, acc[s][0][K].y, acc[s][1][K].x, acc[s][1][K].y));
-      }
-#pragma unroll
-      for (int c = 0; c < CX; c++) acc[s][c][K] = make_float2(0.f, 0.f);
-    }
-  };
-  // all ns^2 x ns cell updates of the point held in `pr`, then roll `pr` on to the row at `ron`;
-  // PH = ring slot of the first plane of the point's window
-  SwrRow<NS> pr;
-  const float *myx = rows + C::KXO + 2 * CX * q;
-  const float *myy = rows + C::KYO + 4 * r;
-  // CLS (SWR_YCLASS builds): 0 = the point's y window ends below row slot S-1, 2 = it starts above
-  // row slot 0, 1 = anything: the untouched slot's FMUL2 + D FFMA2 are not issued at all
-  auto point = [&](auto phc, auto clc, int ron) {
-    constexpr int PH = decltype(phc)::value;
-    constexpr int CLS = decltype(clc)::value;
-    constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
-    float2 wv[S][CX];
-#pragma unroll
-    for (int s = S0; s < S1; s++)
-#pragma unroll
-      for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
-    pr.load_xy(myx, myy, ron);
-#pragma unroll
-    for (int i = 0; i < SwrRow<NS>::NV; i++) {
-#pragma unroll
-      for (int j = 4 * i; j < 4 * i + 4; j++) {
-        if (j < D) {
-          const float2 kzj = pr.kz(j);
-#pragma unroll
-          for (int s = S0; s < S1; s++)
-#pragma unroll
-            for (int c = 0; c < CX; c++)
-              acc[s][c][(PH + j) % D] = fma2(wv[s][c], kzj, acc[s][c][(PH + j) % D]);
-        }
-      }
-      pr.load_kv(rows, ron, i);
-    }
-  };
-
-  int cur = SWR_EMPTY;  // first plane held by the ring
-  int ph = 0;           // ring slot of plane cur
-  int drain = 0;        // planes still to retire before a jump / the end
-  // Two-deep software pipeline over batches of 32 points: the record of batch b+2 and the
-  // strength of batch b+1 (whose address comes from the record of b+1) are in flight while the
-  // warp spreads batch b, so neither DRAM round trip is exposed.
-  const PtRec<float> *recp = a.rec + first + lane;
-  const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
-  // strength (and optional per-point factor) of the point of record rc; the complex product is
-  // taken where the value is consumed, one batch later, so that nothing waits on these gathers
-  auto ldc = [&](const float4 &rc, float2 &sc) {
-    const int o = __float_as_int(rc.w);
-    if (a.scale) sc = __ldg(a.scale + o);
-    return ld_stream2(cin + o);
-  };
-  const float2 zero2 = make_float2(0.f, 0.f);
-  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
-  float4 recB = lane + C::PB < cnt ? ld_stream4(recp + C::PB) : zrec;
-  float2 sA = make_float2(1.f, 0.f), sB = sA;
-  float2 cA = lane < cnt ? ldc(recA, sA) : zero2;
-  for (int b0 = 0; b0 < cnt; b0 += C::PB) {
-    const int nb = min(C::PB, cnt - b0);
-    const bool last = b0 + C::PB >= cnt;
-    const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
-    const float2 cB = b0 + C::PB + lane < cnt ? ldc(recB, sB) : zero2;
-    __syncwarp();
-#if SWR_YCLASS
-    // order the batch by (window plane, y class) so that the phase chain can run class-specialised loops
-    int pos, cls;
-    swr_batch_order<NS>(recA, nb, ya, lane, pos, cls);
-    if (lane < nb) {
-      float2 cv = cA;
-      if (a.scale) cv = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
-      swr_weights<NS>(tab, recA, cv, xa, ya, rows + pos * C::ROW, 2, cls);
-    }
-#else
-    if (lane < nb) {
-      float2 cv = cA;
-      if (a.scale) cv = make_float2(cA.x * sA.x - cA.y * sA.y, cA.x * sA.y + cA.y * sA.x);
-      swr_weights<NS>(tab, recA, cv, xa, ya, rows + lane * C::ROW);
-    }
-#endif
-    __syncwarp();
-    recA = recB;
-    recB = recC;
-    cA = cB;
-    sA = sB;
-    int t = 0, ro = 0;
-    pr.load_xy(myx, myy, 0);
-#pragma unroll
-    for (int i = 0; i < SwrRow<NS>::NV; i++) pr.load_kv(rows, 0, i);
-#if SWR_YCLASS
-#define SWR_ZP(m) ((m) >> 2) /* META = plane * 4 + class */
-#define SWR_SPREAD_POINTS(PH)                                                                   \
-      SWR_SPREAD_CLASS(PH, 0)                                                                   \
-      SWR_SPREAD_CLASS(PH, 1)                                                                   \
-      SWR_SPREAD_CLASS(PH, 2)
-#define SWR_SPREAD_CLASS(PH, CL)                                                                \
-      while (t < nb && zw == 4 * cur + CL) {                                                    \
-        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
-        point(std::integral_constant<int, PH>{}, std::integral_constant<int, CL>{}, ron);       \
-        t++;                                                                                    \
-        ro = ron;                                                                               \
-        zw = pr.zw();                                                                           \
-      }
-#else
-#define SWR_ZP(m) (m)
-#define SWR_SPREAD_POINTS(PH)                                                                   \
-      while (t < nb && zw == cur) {                                                             \
-        const int ron = t + 1 < nb ? ro + C::ROW : ro;                                          \
-        point(std::integral_constant<int, PH>{}, std::integral_constant<int, 1>{}, ron);        \
-        t++;                                                                                    \
-        ro = ron;                                                                               \
-        zw = pr.zw();                                                                           \
-      }
-#endif
-    int zw = pr.zw();
-    if (cur == SWR_EMPTY) cur = SWR_ZP(zw);  // first point: ring empty, ph = 0
-  reenter:
-    for (;;) {
-      switch (ph) {
-#define SWR_SPREAD_PHASE(PH)                                                                    \
-  case PH:                                                                                      \
-    if constexpr (PH < D) {                                                                     \
-      SWR_SPREAD_POINTS(PH)                                                                     \
-      if (t >= nb && !last) {                                                                   \
-        ph = PH;                                                                                \
-        goto batch_done;                                                                        \
-      }                                                                                         \
-      retire(std::integral_constant<int, PH>{}, cur);                                           \
-      cur++;                                                                                    \
-      if (drain) {                                                                              \
-        if (--drain == 0) {                                                                     \
-          if (t >= nb) goto sub_done;                                                           \
-          cur = SWR_ZP(zw); /* ring is empty: re-base the phases on the next point's window */  \
-          ph = 0;                                                                               \
-          goto reenter;                                                                         \
-        }                                                                                       \
-      } else if (t >= nb || (unsigned)(SWR_ZP(zw) - cur + 1) >= (unsigned)D) {                  \
-        drain = D - 1; /* end of the subproblem, or a gap wider than the ring */                \
-      }                                                                                         \
-    }
-        SWR_SPREAD_PHASE(0)
-        SWR_SPREAD_PHASE(1)
-        SWR_SPREAD_PHASE(2)
-        SWR_SPREAD_PHASE(3)
-        SWR_SPREAD_PHASE(4)
-        SWR_SPREAD_PHASE(5)
-        SWR_SPREAD_PHASE(6)
-        SWR_SPREAD_PHASE(7)
-#undef SWR_SPREAD_PHASE
-#undef SWR_SPREAD_POINTS
-#undef SWR_SPREAD_CLASS
-#undef SWR_ZP
-        default: break;
-      }
-      ph = 0;
-    }
-  batch_done:;
-  }
-sub_done:;
-}
 
 // ==================================================================================== INTERP
 // Per-warp shared memory: the weight rows + RES[16][33] float2 partial results of half a batch
