@@ -180,6 +180,23 @@ int b2n_slab_partition(int is_double, void *stream, int64_t M, const void *p0, c
                        const void *p2, const void *c, int64_t nf0, int world, int halo, void *o0,
                        void *o1, void *o2, void *oc, void *counts2);
 
+/* The uniform-grid stages of a type 1 whose fine grid is distributed over the GPUs in z-slabs
+ * (parallel.py: slab_pencil_fft; SURVEY.md 8(e) native path; the reference's equivalent is the
+ * replicated FFT + psum of tests/sharding_test.py:163-165).  All work is enqueued on `stream`;
+ * cuFFT plans and kernel series are cached per geometry.
+ *  b2n_slab_fft_xy: `slab` = this rank's nzl planes (nzl, nf2, nf1), transformed IN PLACE over
+ *    (y, x); `send` (nzl * n2 * n1 complex) receives the n1 x n2 central modes divided by the x / y
+ *    kernel series (index maps: V/src/cuda/deconvolve_wrapper.cu:76-118), grouped by the rank that
+ *    owns their y range (contiguous blocks, the first n2 % world ranks one row longer):
+ *    send[dst][z][y - lo(dst)][x] -- the operand of one all_to_all.
+ *  b2n_slab_fft_z: `pencil` = the received block (nf3, plane = n2_local * n1), z-major,
+ *    transformed IN PLACE along z; out (n3, n2_local, n1) = its n3 central modes / z series. */
+int b2n_slab_fft_xy(int is_double, void *stream, void *slab, int64_t nzl, int64_t nf2, int64_t nf1,
+                    int64_t n2, int64_t n1, int world, int iflag, int modeord, int ns, double beta,
+                    void *send);
+int b2n_slab_fft_z(int is_double, void *stream, void *pencil, int64_t nf3, int64_t n3, int64_t plane,
+                   int iflag, int modeord, int ns, double beta, void *out);
+
 /* Per-stage device timings (ms) of the most recent b2n_execute / b2n_setpts on this plan when
  * opts.debug != 0: [0] sort, [1] spread, [2] fft, [3] deconvolve/amplify, [4] interp,
  * [5] type-3 pre/post, [6] memset. */

@@ -196,6 +196,8 @@ def slab_pencil_fft(slab, output_shape, nf, iflag, ns, beta, modeord=0, group=No
     world, rank = _world(group)
     N3, N2, N1 = (int(n) for n in output_shape)
     nf3, nf2, nf1 = (int(n) for n in nf)
+    if slab.is_cuda:
+        return _slab_pencil_fft_native(slab, (N3, N2, N1), (nf3, nf2, nf1), iflag, ns, beta, modeord, group, gather)
     rdt = torch.float32 if slab.dtype == torch.complex64 else torch.float64
     dev = slab.device
     idx = {}
@@ -230,6 +232,44 @@ def slab_pencil_fft(slab, output_shape, nf, iflag, ns, beta, modeord=0, group=No
         pencil = s2
     pencil = torch.fft.ifft(pencil, dim=0, norm="forward") if iflag >= 0 else torch.fft.fft(pencil, dim=0)
     out = pencil.index_select(0, idx["z"]) * dec["z"][:, None, None]
+    if gather and world > 1:
+        out = _all_gather_cat(out, group, 1, ysz)
+    return out
+
+
+def _slab_pencil_fft_native(slab, N, nf, iflag, ns, beta, modeord, group, gather):
+    """slab_pencil_fft on the device: the two stages are library calls (csrc/slab.cu: cuFFT plans cached
+    per geometry, fused crop + deconvolve kernels), the transpose between them is ONE all_to_all whose
+    split sizes follow from the shapes -- nothing is read back to the host, the slab is transformed in
+    place."""
+    world, rank = _world(group)
+    N3, N2, N1 = N
+    nf3, nf2, nf1 = nf
+    L = _lib.lib()
+    vp = C.c_void_p
+    dbl = int(slab.dtype == torch.complex128)
+    slab = slab.contiguous()
+    nzl = slab.shape[0]
+    assert slab.shape[1:] == (nf2, nf1) and nzl * world == nf3
+    st = vp(torch.cuda.current_stream(slab.device).cuda_stream)
+    ysz = [b - a for a, b in (shard_range(N2, world, r) for r in range(world))]
+    send = torch.empty(nzl * N2 * N1, dtype=slab.dtype, device=slab.device)
+    ier = L.b2n_slab_fft_xy(dbl, st, vp(slab.data_ptr()), nzl, nf2, nf1, N2, N1, world, int(iflag), int(modeord),
+                            int(ns), float(beta), vp(send.data_ptr()))
+    if ier:
+        raise RuntimeError(f"b2n_slab_fft_xy failed with code {ier}")
+    if world > 1:
+        recv = torch.empty(nf3 * ysz[rank] * N1, dtype=slab.dtype, device=slab.device)
+        dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send),
+                               output_split_sizes=[nzl * ysz[rank] * N1] * world,
+                               input_split_sizes=[nzl * ysz[d] * N1 for d in range(world)], group=group)
+    else:
+        recv = send
+    out = torch.empty((N3, ysz[rank], N1), dtype=slab.dtype, device=slab.device)
+    ier = L.b2n_slab_fft_z(dbl, st, vp(recv.data_ptr()), nf3, N3, ysz[rank] * N1, int(iflag), int(modeord), int(ns),
+                           float(beta), vp(out.data_ptr()))
+    if ier:
+        raise RuntimeError(f"b2n_slab_fft_z failed with code {ier}")
     if gather and world > 1:
         out = _all_gather_cat(out, group, 1, ysz)
     return out

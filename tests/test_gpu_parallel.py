@@ -112,6 +112,24 @@ def test_native_type1_pipeline_single_gpu(nm, iflag):
     assert oracle.relerr(a.cpu().numpy(), want) < 2e-5
 
 
+@pytest.mark.parametrize("N,modeord,iflag,dt", [((12, 10, 16), 0, 1, torch.complex64), ((9, 15, 7), 1, -1, torch.complex64),
+                                                 ((8, 8, 8), 0, -1, torch.complex128)])
+def test_native_slab_pencil_fft_equals_the_torch_restatement(N, modeord, iflag, dt):
+    """csrc/slab.cu (b2n_slab_fft_xy / b2n_slab_fft_z: cuFFT + fused crop/deconvolve kernels) against the
+    torch implementation of the same stages that the gloo tests exercise (tests/test_parallel.py)."""
+    from jax_finufft_b200 import parallel as P
+
+    ns, beta, nf = P.fine_grid_geometry(N, 1e-6, dt == torch.complex64)
+    g = torch.Generator().manual_seed(3)
+    rdt = torch.float32 if dt == torch.complex64 else torch.float64
+    slab = torch.complex(torch.rand(nf, generator=g, dtype=rdt) - 0.5, torch.rand(nf, generator=g, dtype=rdt) - 0.5)
+    want = P.slab_pencil_fft(slab.clone(), N, nf, iflag, ns, beta, modeord=modeord)            # CPU tensors: torch glue
+    got = P.slab_pencil_fft(slab.clone().cuda(), N, nf, iflag, ns, beta, modeord=modeord)       # CUDA: the library
+    assert got.shape == want.shape == tuple(N)
+    err = float(torch.linalg.vector_norm(got.cpu() - want) / torch.linalg.vector_norm(want))
+    assert err < (2e-6 if dt == torch.complex64 else 1e-13), err
+
+
 def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
