@@ -435,7 +435,8 @@ def nufft1_sharded_points(output_shape, source_local, *points_local, group=None,
     range; ``source_local`` (M_local,) and ``points_local`` are this rank's shard.
 
     combine="psum"            reference-equivalent: local nufft1 + all_reduce of the modes
-                              (sharding_test.py:163-165).  Output replicated.
+                              (sharding_test.py:163-165).  Output replicated (with an explicit
+                              combine="psum", whatever ``gather`` says; the collective is outside autograd).
     combine="reduce_scatter"  native path (module docstring).  3-D, single transform.  Output
                               y-sharded (N3, N2_local, N1) unless ``gather``.
     combine="slab"            spatial split (module docstring): points exchanged by z-slab, spread
@@ -452,6 +453,8 @@ def nufft1_sharded_points(output_shape, source_local, *points_local, group=None,
     if combine == "psum" or len(points_local) != 3 or source_local.ndim != 1:
         out = nufft1(output_shape, source_local, *points_local, iflag=iflag, eps=eps, opts=opts)
         if world > 1:
+            # the collective is not differentiable: reduce a detached copy, never the autograd output in place
+            out = out.detach().clone() if out.requires_grad else out
             dist.all_reduce(torch.view_as_real(out), group=group)
         return out
     if combine not in ("reduce_scatter", "slab"):
@@ -462,9 +465,13 @@ def nufft1_sharded_points(output_shape, source_local, *points_local, group=None,
     single = source_local.dtype == torch.complex64
     ns, beta, nf = fine_grid_geometry(output_shape, eps, single, upsampfac=o.gpu_upsampfac,
                                       kerevalmeth=int(o.gpu_kerevalmeth))
-    if nf[0] % world:
-        return nufft1_sharded_points(output_shape, source_local, *points_local, group=group, combine="psum",
-                                     iflag=iflag, eps=eps, opts=opts)
+    if nf[0] % world:  # the slabs do not divide: psum, but keep the layout the caller asked for
+        out = nufft1_sharded_points(output_shape, source_local, *points_local, group=group, combine="psum",
+                                    iflag=iflag, eps=eps, opts=opts)
+        if not gather and world > 1:
+            ylo, yhi = shard_range(int(output_shape[1]), world, _world(group)[1])
+            out = out[:, ylo:yhi].contiguous()
+        return out
     if combine == "slab" and nf[0] // world >= 2 * slab_halo(ns):
         src, pts, Lz = exchange_points_by_slab(source_local, list(points_local), nf[0], ns, group)
         local = _spread_only((Lz, nf[1], nf[2]), src, pts, eps, iflag, o.gpu_upsampfac)
