@@ -197,6 +197,19 @@ int b2n_slab_fft_xy(int is_double, void *stream, void *slab, int64_t nzl, int64_
 int b2n_slab_fft_z(int is_double, void *stream, void *pencil, int64_t nf3, int64_t n3, int64_t plane,
                    int iflag, int modeord, int ns, double beta, void *out);
 
+/* The per-point stacks and reductions of the JVP / VJP rules (ref src/jax_finufft/ops.py:238-273,
+ * 280-314: jnp.stack([c, dx*c, dy*c, dz*c], axis=2) and sum(conj(c) * h_d)), one fused pass each.
+ *  b2n_stack_scaled: src complex [n_tot][n_transf][n]; scales[k], k < n_scale <= 4: real
+ *    [n_tot][n] shared by the n_transf transforms, or NULL (factor 1);
+ *    out[i][t][k][j] = scales[k][i][j] * src[i][t][j]   -- the operand of the stacked transform.
+ *  b2n_grad_points: c complex [n_tot][n_transf][n]; h complex [n_tot][n_transf][n_comp][n];
+ *    out[k][i][j] = sign * sum_t Im(conj(c[i][t][j]) * h[i][t][first + k][j])   (mode 0; mode 1: Re),
+ *    k < count <= 4 -- the cotangents of the point coordinates. */
+int b2n_stack_scaled(int is_double, void *stream, int64_t n_tot, int n_transf, int64_t n, int n_scale,
+                     const void *src, const void *const *scales, void *out);
+int b2n_grad_points(int is_double, void *stream, int64_t n_tot, int n_transf, int64_t n, int n_comp,
+                    int first, int count, int mode, double sign, const void *c, const void *h, void *out);
+
 /* Per-stage device timings (ms) of the most recent b2n_execute / b2n_setpts on this plan when
  * opts.debug != 0: [0] sort, [1] spread, [2] fft, [3] deconvolve/amplify, [4] interp,
  * [5] type-3 pre/post, [6] memset. */

@@ -66,6 +66,7 @@ EXPORTED = [
     "b2n_fseries", "b2n_horner_table", "b2n_default_binsize", "b2n_version", "b2n_launch_count",
     "b2n_ffi_call", "b2n_ffi_arity", "b2n_ffi_targets", "b2n_strerror", "b2n_set_setpts_cache", "b2n_slab_partition",
     "b2n_set_cache_limit", "b2n_cache_bytes", "b2n_slab_fft_xy", "b2n_slab_fft_z",
+    "b2n_stack_scaled", "b2n_grad_points",
 ]
 
 
@@ -118,6 +119,8 @@ def lib():
         L.b2n_slab_partition.argtypes = [ci, vp, i64, vp, vp, vp, vp, i64, ci, ci, vp, vp, vp, vp, vp]
         L.b2n_set_setpts_cache.restype = ci
         L.b2n_slab_fft_xy.argtypes = [ci, vp, vp, i64, i64, i64, i64, i64, ci, ci, ci, ci, dbl, vp]
+        L.b2n_stack_scaled.argtypes = [ci, vp, i64, ci, i64, ci, vp, C.POINTER(vp), vp]
+        L.b2n_grad_points.argtypes = [ci, vp, i64, ci, i64, ci, ci, ci, ci, dbl, vp, vp, vp]
         L.b2n_slab_fft_z.argtypes = [ci, vp, vp, i64, i64, i64, ci, ci, ci, dbl, vp]
         L.b2n_setup_spreader.argtypes = [dbl, dbl, ci, ci, C.POINTER(ci), C.POINTER(dbl)]
         L.b2n_next235beven.argtypes = [i64, i64]

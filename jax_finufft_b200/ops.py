@@ -53,6 +53,54 @@ def _freq(n, modeord, dim, ndim, like):
     return k.to(like.real.dtype).reshape(shape)
 
 
+# ---------------------------------------------------------------- fused stacks / reductions (csrc/gradstack.cu)
+def _stack_scaled(base, scales):
+    """torch.stack([s[:, None, :] * base  (or base for s is None)  for s in scales], dim=2) in ONE pass:
+    base (n_tot, n_transf, n) complex, each scale (n_tot, n) real.  The operand the JVP / VJP rules hand
+    to their stacked transform (ref ops.py:254,269)."""
+    if not base.is_cuda or len(scales) > 4:
+        return torch.stack([base if sc is None else sc[:, None, :] * base for sc in scales], dim=2)
+    import ctypes as C
+    from . import _lib
+
+    base = base.contiguous()
+    n_tot, n_transf, n = base.shape
+    rdt = base.real.dtype
+    sc = [None if t is None else t.to(rdt).contiguous() for t in scales]
+    out = torch.empty((n_tot, n_transf, len(sc), n), dtype=base.dtype, device=base.device)
+    ptrs = (C.c_void_p * len(sc))(*[None if t is None else t.data_ptr() for t in sc])
+    with torch.cuda.device(base.device):
+        ier = _lib.lib().b2n_stack_scaled(int(base.dtype == torch.complex128),
+                                          C.c_void_p(torch.cuda.current_stream(base.device).cuda_stream),
+                                          n_tot, n_transf, n, len(sc), C.c_void_p(base.data_ptr()), ptrs,
+                                          C.c_void_p(out.data_ptr()))
+    if ier:
+        raise RuntimeError(f"b2n_stack_scaled failed with code {ier}")
+    return out
+
+
+def _grad_points(c, h, first, count, sign, real_part=False):
+    """[sign * (c.conj() * h[:, :, first + k]).imag.sum(dim=1) for k < count] in ONE pass (real_part: .real):
+    c (n_tot, n_transf, n), h (n_tot, n_transf, K, n) -> list of (n_tot, n) real tensors."""
+    if not c.is_cuda or count > 4:
+        part = (lambda z: z.real) if real_part else (lambda z: z.imag)
+        return [sign * part(c.conj() * h[:, :, first + k]).sum(dim=1) for k in range(count)]
+    import ctypes as C
+    from . import _lib
+
+    c, h = c.contiguous(), h.contiguous()
+    n_tot, n_transf, n = c.shape
+    out = torch.empty((count, n_tot, n), dtype=c.real.dtype, device=c.device)
+    with torch.cuda.device(c.device):
+        ier = _lib.lib().b2n_grad_points(int(c.dtype == torch.complex128),
+                                         C.c_void_p(torch.cuda.current_stream(c.device).cuda_stream), n_tot, n_transf, n,
+                                         h.shape[2], int(first), int(count), 1 if real_part else 0, float(sign),
+                                         C.c_void_p(c.data_ptr()), C.c_void_p(h.data_ptr()), C.c_void_p(out.data_ptr()))
+    if ier:
+        raise RuntimeError(f"b2n_grad_points failed with code {ier}")
+    return list(out.unbind(0))
+
+
 class _NufftPrimitive(torch.autograd.Function):
     """nufft{1,2,3}_p of the reference (ops.py:356-386) on canonical operands."""
 
@@ -94,8 +142,9 @@ class _NufftPrimitive(torch.autograd.Function):
                 off = 0
                 if need[0]:
                     grad_source, off = h[:, :, 0], 1
-                for n, d in enumerate(dims):  # dL/dx = iflag * Im(conj(c) * h_d), summed over transforms
-                    grad_points[d] = iflag * (source.conj() * h[:, :, off + n]).imag.sum(dim=1)
+                if dims:  # dL/dx = iflag * Im(conj(c) * h_d), summed over transforms
+                    for d, gp in zip(dims, _grad_points(source, h, off, len(dims), iflag)):
+                        grad_points[d] = gp
         elif nufft_type == 2:
             ndim = len(points)
             if need[0]:
@@ -105,29 +154,29 @@ class _NufftPrimitive(torch.autograd.Function):
                 fopts = options.unpack_opts(opts, 2, True)
                 args = [(1j * iflag) * _freq(source.shape[2 + d], modeord, d, ndim, source) * source for d in dims]
                 h = nufft2(torch.stack(args, dim=2), *map(exp, points), iflag=iflag, eps=eps, opts=fopts)
-                for n, d in enumerate(dims):
-                    grad_points[d] = (g.conj() * h[:, :, n]).real.sum(dim=1)
+                for d, gp in zip(dims, _grad_points(g, h, 0, len(dims), 1.0, real_part=True)):
+                    grad_points[d] = gp
         else:
             ndim = len(points) // 2
             x, s = points[:ndim], points[ndim:]
-            stack = [g] if need[0] else []
             dims = [d for d in range(ndim) if need[1 + d]]
-            for d in dims:
-                stack.append(s[d][:, None, :] * g)
-            if stack:
-                h = nufft3(torch.stack(stack, dim=2), *map(exp, s), *map(exp, x), iflag=-iflag, eps=eps, opts=bopts)
+            scales = ([None] if need[0] else []) + [s[d] for d in dims]   # the stack [g, s_x g, s_y g, s_z g]
+            if scales:
+                h = nufft3(_stack_scaled(g, scales), *map(exp, s), *map(exp, x), iflag=-iflag, eps=eps, opts=bopts)
                 off = 0
                 if need[0]:
                     grad_source, off = h[:, :, 0], 1
-                for n, d in enumerate(dims):
-                    grad_points[d] = iflag * (source.conj() * h[:, :, off + n]).imag.sum(dim=1)
+                if dims:
+                    for d, gp in zip(dims, _grad_points(source, h, off, len(dims), iflag)):
+                        grad_points[d] = gp
             tdims = [d for d in range(ndim) if need[1 + ndim + d]]
             if tdims:
                 fopts = options.unpack_opts(opts, 3, True)
-                args = [x[d][:, None, :] * source for d in tdims]
-                h = nufft3(torch.stack(args, dim=2), *map(exp, x), *map(exp, s), iflag=iflag, eps=eps, opts=fopts)
-                for n, d in enumerate(tdims):  # Re(conj(g) * i*iflag * h) = -iflag * Im(conj(g) * h)
-                    grad_points[ndim + d] = -iflag * (g.conj() * h[:, :, n]).imag.sum(dim=1)
+                h = nufft3(_stack_scaled(source, [x[d] for d in tdims]), *map(exp, x), *map(exp, s), iflag=iflag,
+                           eps=eps, opts=fopts)
+                # Re(conj(g) * i*iflag * h) = -iflag * Im(conj(g) * h)
+                for d, gp in zip(tdims, _grad_points(g, h, 0, len(tdims), -iflag)):
+                    grad_points[ndim + d] = gp
         return (None, None, None, None, None, grad_source, *grad_points)
 
     # ---------------------------------------------------------------- forward mode (ops.py:158-277)
