@@ -26,7 +26,7 @@ def T(a):
     return torch.as_tensor(np.ascontiguousarray(a), device="cuda")
 
 
-def _run(typ, nm, M, eps, ntr, iflag, modeord, seed, seam=False):
+def _run(typ, nm, M, eps, ntr, iflag, modeord, seed, seam=False, upsampfac=2.0):
     from jax_finufft_b200.plan import Plan
 
     dim = len(nm)
@@ -41,16 +41,16 @@ def _run(typ, nm, M, eps, ntr, iflag, modeord, seed, seam=False):
         data = (rng.uniform(-1, 1, (ntr, M)) + 1j * rng.uniform(-1, 1, (ntr, M))).astype(np.complex64)
     else:
         data = (rng.uniform(-1, 1, (ntr,) + nm[::-1]) + 1j * rng.uniform(-1, 1, (ntr,) + nm[::-1])).astype(np.complex64)
-    p = Plan(typ, nm, n_trans=ntr, eps=eps, isign=iflag, modeord=modeord, upsampfac=2.0)
+    p = Plan(typ, nm, n_trans=ntr, eps=eps, isign=iflag, modeord=modeord, upsampfac=upsampfac)
     p.setpts(*[T(x) for x in pts])
     out = p.execute(T(data)).cpu().numpy()
     info = p.info()
     p.destroy()
     p64 = [x.astype(np.float64) for x in pts]
     if typ == 1:
-        want = oracle.nufft1(nm, data, *p64, iflag=iflag, eps=eps, modeord=modeord, prec=1)
+        want = oracle.nufft1(nm, data, *p64, iflag=iflag, eps=eps, modeord=modeord, prec=1, upsampfac=upsampfac)
     else:
-        want = oracle.nufft2(data, *p64, iflag=iflag, eps=eps, modeord=modeord, prec=1)
+        want = oracle.nufft2(data, *p64, iflag=iflag, eps=eps, modeord=modeord, prec=1, upsampfac=upsampfac)
     return out, want, info
 
 
@@ -88,3 +88,27 @@ def test_stacked_transforms_register_kernels(dim, typ, ntr):
     assert out.shape == want.shape
     for t in range(ntr):
         assert oracle.relerr(out[t], want[t]) < G.parity_tol(1e-5, False), (dim, typ, ntr, t)
+
+
+@pytest.mark.parametrize("eps", [1e-2, 1e-3, 1e-4, 1e-5, 1e-6])   # ns = 3 .. 7: every instantiation of k_rt2s_spread
+@pytest.mark.parametrize("ntr", [2, 8, 11])
+def test_stacked_2d_type1_narrow_window_all_widths(eps, ntr):
+    """2-D type 1 with stacked transforms runs the narrow-window stacked spreader (8 transforms per
+    pass, packed strengths): one full pass, a partial one, and more transforms than a batch holds."""
+    out, want, info = _run(1, (44, 30), 40000, eps, ntr, 1, 0, 300 + ntr, seam=True)
+    assert info.method == 3
+    for t in range(ntr):
+        err = oracle.relerr(out[t], want[t])
+        assert err < G.parity_tol(eps, False), (eps, ntr, t, err)
+
+
+@pytest.mark.parametrize("typ", [1, 2])
+@pytest.mark.parametrize("nm", [(40, 36), (40, 36, 32)])
+def test_register_kernels_low_upsampling(nm, typ):
+    """upsampfac = 1.25 gives kernel tables with another coefficient count than the ones the 3-D
+    spreader unrolls: the run-time Horner loop of swr2_weights."""
+    out, want, info = _run(typ, nm, 60000, 1e-4, 1, -1, 0, 77, seam=True, upsampfac=1.25)
+    err = oracle.relerr(out, want)
+    print(f"\nPARITY sigma=1.25 {'x'.join(map(str, nm))} t{typ}: {err:.3e} method {info.method}")
+    assert info.method == 3, "expected the register kernels"
+    assert err < G.parity_tol(1e-4, False), err
