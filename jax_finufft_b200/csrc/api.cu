@@ -117,6 +117,9 @@ template <typename T> Plan<T>::~Plan() {
   dev_free(pts.sig, st);
   dev_free(prephase, st);
   dev_free(deconv, st);
+  if (side) cudaStreamDestroy(side);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
   if (has_fft) cufftDestroy(fft);
   if (pruned) { cufftDestroy(fft_z); for (int k = 0; k < 2; k++) if (slab_n[k]) cufftDestroy(fft_xy[k]); }
   delete inner;
@@ -199,6 +202,17 @@ int Plan<T>::init(int type_, int dim_, const int64_t *n_modes, int iflag_, int n
     for (int d = 0; d < dim; d++)
       nf[d] = opts.gpu_spreadinterponly ? ms[d] : set_nf_type12(ms[d], sigma, ns);
     if (int e = alloc_grid()) return e;
+    if (!opts.gpu_spreadinterponly && !opts.debug && !getenv("B2N_NO_OVERLAP")) {  // side stream of overlap_begin
+      int prio_lo = 0, prio_hi = 0;  // highest priority: its blocks go first whenever the sort's leave room
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      if (cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (side) cudaStreamDestroy(side);
+        side = nullptr;
+      }
+    }
   }
   if (opts.debug)
     fprintf(stderr, "[b200nufft] plan: type %d dim %d %s eps=%.3g sigma=%.3g ns=%d beta=%.4g ncoef=%d method=%s "
@@ -469,6 +483,26 @@ template <typename T> int Plan<T>::exec_phase(int phase, void *cv, void *fkv) {
   }
   return 0;
 }
+
+template <typename T> bool Plan<T>::overlap_begin(void *c, void *fk, cudaEvent_t wait_first, int *err) {
+  *err = 0;
+  // worth a fork only when the grid stages are not tiny (two event operations + a stream switch)
+  if (!side || type == 3 || ntransf > batch || opts.gpu_spreadinterponly || opts.debug ||
+      (size_t)nftot * sizeof(cpx<T>) < (size_t(32) << 20))
+    return false;
+  cudaStream_t main_st = stream;
+  if (cudaEventRecord(ev_fork, main_st) != cudaSuccess || cudaStreamWaitEvent(side, ev_fork, 0) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (wait_first && type == 2) cudaStreamWaitEvent(side, wait_first, 0);  // the modes, when they come from the host
+  set_stream(side);
+  *err = exec_phase(PH_BEGIN, c, fk);
+  set_stream(main_st);
+  if (cudaEventRecord(ev_join, side) != cudaSuccess) *err = *err ? *err : B2N_ERR_CUDA_FAILURE;
+  return true;
+}
+template <typename T> void Plan<T>::overlap_join() { cudaStreamWaitEvent(stream, ev_join, 0); }
 
 // Chunk geometry for a host-resident point set: enough chunks that the copy of chunk k+1 hides
 // the bin-sort + spread/interp of chunk k, few enough that a chunk still fills the bins (the
@@ -1059,18 +1093,23 @@ static int run_core(int type, int dim, int is_double, cudaStream_t stream, doubl
       P[d] = (const char *)pts[d] + (size_t)index * n_j * rs;
       if (type == 3) Tg[d] = (const char *)tgt[d] + (size_t)index * n_k_total * rs;
     }
-    int ret = p->setpts(n_j, P[0], P[1], P[2], type == 3 ? n_k_total : 0, Tg[0], Tg[1], Tg[2]);
+    const char *s_i = (const char *)src + (size_t)index * n_src * n_transf * cs;
+    char *o_i = (char *)out + (size_t)index * n_out * n_transf * cs;
+    // c = nonuniform side, fk = uniform side (or type-3 targets)
+    void *c_i = type == 2 ? (void *)o_i : (void *)s_i, *fk_i = type == 2 ? (void *)s_i : (void *)o_i;
+    // the grid stages that do not need the points run beside the bin-sort (PlanBase::overlap_begin)
+    int oerr = 0;
+    const bool overlapped = p->overlap_begin(c_i, fk_i, index == 0 ? src_ready : nullptr, &oerr);
+    int ret = oerr ? oerr : p->setpts(n_j, P[0], P[1], P[2], type == 3 ? n_k_total : 0, Tg[0], Tg[1], Tg[2]);
+    if (overlapped) p->overlap_join();
     if (ret != 0) {
       cudaStreamSynchronize(stream);
       delete p;
       return ret;
     }
     if (src_ready && index == 0) cudaStreamWaitEvent(stream, src_ready, 0);
-    const char *s_i = (const char *)src + (size_t)index * n_src * n_transf * cs;
-    char *o_i = (char *)out + (size_t)index * n_out * n_transf * cs;
-    // execute(c, fk): c = nonuniform side, fk = uniform side (or type-3 targets)
-    if (type == 2) ret = p->execute((void *)o_i, (void *)s_i);
-    else ret = p->execute((void *)s_i, (void *)o_i);
+    if (overlapped) ret = p->exec_phase(PlanBase::PH_BODY | PlanBase::PH_END, c_i, fk_i);
+    else ret = p->execute(c_i, fk_i);
     if (ret != 0) {
       cudaStreamSynchronize(stream);
       delete p;

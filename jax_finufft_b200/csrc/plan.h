@@ -57,6 +57,13 @@ struct PlanBase {
   enum { PH_BEGIN = 1, PH_BODY = 2, PH_END = 4 };
   virtual int exec_phase(int phase, void *c, void *fk) = 0;
   virtual bool can_chunk(int64_t M, int *nchunk, int64_t *chunk) const = 0;
+  // What precedes the non-uniform stage (PH_BEGIN: type 1 clears the fine grid, type 2 amplifies
+  // and FFTs the modes) does not depend on the points: b2n_run starts it on the plan's side stream
+  // BEFORE the bin-sort and joins it afterwards, so the two overlap (the sort is bound by atomics
+  // and latency, amplify + FFT by DRAM bandwidth).  overlap_begin returns false if the plan cannot
+  // (type 3, more transforms than a batch, spread/interp only, debug timers on).
+  virtual bool overlap_begin(void *c, void *fk, cudaEvent_t wait_first, int *err) = 0;
+  virtual void overlap_join() = 0;
   virtual void info(b2n_plan_info *out) = 0;
   virtual int sort_get(const int32_t **idx, const int32_t **bin_start, int64_t *nbins) = 0;
   virtual void set_stream(cudaStream_t s) = 0;
@@ -91,6 +98,8 @@ template <typename T> struct Plan : PlanBase {
   int64_t cap_cpack = 0;
   HornerTable<T> tab;
   cudaStream_t stream = 0;
+  cudaStream_t side = nullptr;             // overlap_begin / overlap_join
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   T *fwker[3] = {nullptr, nullptr, nullptr};  // kernel Fourier series, nf_d/2+1 each
   cpx<T> *fw = nullptr;                       // fine grid(s): batch * nftot
@@ -129,6 +138,8 @@ template <typename T> struct Plan : PlanBase {
   int execute(void *c, void *fk) override;
   int exec_phase(int phase, void *c, void *fk) override;
   bool can_chunk(int64_t M, int *nchunk, int64_t *chunk) const override;
+  bool overlap_begin(void *c, void *fk, cudaEvent_t wait_first, int *err) override;
+  void overlap_join() override;
   int spread(const cpx<T> *c, const cpx<T> *prescale, cpx<T> *grid, int ntr);
   int interp(cpx<T> *c, const cpx<T> *postscale, const cpx<T> *grid, int ntr);
   int exec1(cpx<T> *c, cpx<T> *fk);
