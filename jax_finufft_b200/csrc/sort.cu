@@ -96,6 +96,7 @@ void dev_free(void *p, cudaStream_t st) {
 // Setpts cache: every kernel of the sort takes a device flag and returns at once when it is set
 // (the flag is uniform over the grid and read before any barrier).  See binsort_points.
 #define B2N_SKIP_IF(p) do { if ((p) != nullptr && *(p) != 0) return; } while (0)
+#define B2N_GATE(g) do { if ((g).gate != nullptr && *(g).gate != (g).gate_val) return; } while (0)
 
 // ------------------------------------------------------------------------------- scan (int32)
 constexpr int SCAN_T = 256;
@@ -236,6 +237,10 @@ struct SortGeom {
   int swr_ns;  // 0: reference bins (floor of the folded coordinate); else bins of ANCHOR cells
   unsigned magic[3];  // ceil(2^32 / bin[d]) (0 for bin 1): u / bin = umulhi(u, magic), u < 2^26
   const int *skip;    // setpts cache: non-zero = these points are already sorted in the plan (or null)
+  // two-pass sort (binsort_points): the fast passes run while *gate == 0 (no bucket overflowed), the
+  // three-pass fallback only once it is 1; null = unconditional
+  const int *gate;
+  int gate_val;
 };
 
 // u / g.bin[d] without an integer division (the three runtime divides were a third of the
@@ -306,6 +311,7 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
                                                    const T *__restrict__ y, const T *__restrict__ z,
                                                    int32_t *__restrict__ hist, int32_t *__restrict__ dupes) {
   B2N_SKIP_IF(g.skip);
+  B2N_GATE(g);
   __shared__ int tkey[HT_N], tcnt[HT_N];
   __shared__ int used;    // lanes merged in this CTA
   __shared__ int filled;  // the table holds entries
@@ -368,15 +374,31 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
 constexpr int PT_T = 256;
 template <typename T> struct PartCfg { static constexpr int E = sizeof(T) == 4 ? 8 : 4; };
 
-template <typename T>
+// FAST (two-pass sort): there is no histogram yet.  Bucket b owns the fixed region [b * cap,
+// (b + 1) * cap) of tmp; a run that does not fit raises *ovf (every later CTA then returns at once
+// and the three-pass pipeline takes over), and the fine key histogram is taken here, one RED per
+// record, beside the staging -- the separate histogram pass (0.96 ms at C3) repeated this kernel's
+// whole per-point instruction stream (loads, fold_rescale, key) just to count.
+template <typename T, bool FAST>
 __global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const T *__restrict__ x,
                                                      const T *__restrict__ y,
                                                      const T *__restrict__ z,
                                                      const int32_t *__restrict__ key_start,
                                                      int64_t K, int shift, int nbuckets,
                                                      int32_t *__restrict__ bucket_cur,
-                                                     PtRec<T> *__restrict__ tmp) {
+                                                     PtRec<T> *__restrict__ tmp, int cap,
+                                                     int32_t *__restrict__ hist, int *__restrict__ ovf) {
   B2N_SKIP_IF(g.skip);
+  if (FAST) {
+    // *ovf changes WHILE this kernel runs: the whole CTA must take one decision (threads that read
+    // it at different moments would otherwise part ways in front of a barrier)
+    __shared__ int go;
+    if (threadIdx.x == 0) go = *reinterpret_cast<volatile int *>(ovf) == 0;
+    __syncthreads();
+    if (!go) return;
+  } else {
+    B2N_GATE(g);
+  }
   constexpr int E = PartCfg<T>::E, N = PT_T * E;
   __shared__ PtRec<T> srec[N];
   __shared__ unsigned short perm[N];
@@ -394,7 +416,9 @@ __global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const
     if (sl < nloc) {
       T xr, yr, zr;
       fold3(g, c0 + sl, x, y, z, xr, yr, zr);
-      const int bkt = point_key(g, xr, yr, zr) >> shift;
+      const int key = point_key(g, xr, yr, zr);
+      if (FAST) atomicAdd(&hist[key], 1);
+      const int bkt = key >> shift;
       br[e] = (bkt << 16) | atomicAdd(&cnt[bkt], 1);
       srec[sl] = make_rec<T>(xr, yr, zr, c0 + sl);
     }
@@ -416,8 +440,14 @@ __global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const
     for (int w = 0; w < PT_T / 32; w++) pre += w < wid ? wsum[w] : 0;
     off[threadIdx.x] = pre + inc - v;
     if (threadIdx.x < nbuckets && v > 0) {
-      const int64_t k0 = (int64_t)threadIdx.x << shift;
-      base[threadIdx.x] = key_start[k0 < K ? k0 : K] + atomicAdd(&bucket_cur[threadIdx.x], v);
+      if (FAST) {
+        const int at = atomicAdd(&bucket_cur[threadIdx.x], v);
+        base[threadIdx.x] = at + v <= cap ? (int)threadIdx.x * cap + at : -1;
+        if (at + v > cap) atomicExch(ovf, 1);
+      } else {
+        const int64_t k0 = (int64_t)threadIdx.x << shift;
+        base[threadIdx.x] = key_start[k0 < K ? k0 : K] + atomicAdd(&bucket_cur[threadIdx.x], v);
+      }
     }
   }
   __syncthreads();
@@ -435,7 +465,7 @@ __global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const
     const int j = e * PT_T + threadIdx.x;
     if (j < nloc) {
       const int b = pbkt[j];
-      tmp[base[b] + (j - off[b])] = srec[perm[j]];
+      if (!FAST || base[b] >= 0) tmp[base[b] + (j - off[b])] = srec[perm[j]];
     }
   }
 }
@@ -447,17 +477,25 @@ __global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const
 // latency overlaps (all PL_E of them).
 constexpr int PL_G = 8;  // points per thread in flight (4: 1.64 ms, 8: 1.44 ms, 16: 2.2 ms at C3)
 constexpr int PL_E = 8;  // points per thread; consecutive chunks per CTA keep the L2 window small
-template <typename T, bool RAW>
+// PADDED (two-pass sort): tmp holds bucket b in [b * cap, b * cap + bucket_cnt[b]); a CTA's 2048 slots lie
+// inside one bucket (cap is a multiple of 2048), M = end of that bucket's records.
+template <typename T, bool RAW, bool PADDED = false>
 __global__ void __launch_bounds__(256) k_place(SortGeom g, int64_t M, const T *__restrict__ x,
                                                 const T *__restrict__ y, const T *__restrict__ z,
                                                 const PtRec<T> *__restrict__ tmp,
                                                 int32_t *__restrict__ key_cursor,
                                                 PtRec<T> *__restrict__ out,
-                                                const int32_t *__restrict__ dupes, int64_t dupe_limit) {
+                                                const int32_t *__restrict__ dupes, int64_t dupe_limit,
+                                                int cap = 0, const int32_t *__restrict__ bucket_cnt = nullptr) {
   B2N_SKIP_IF(g.skip);
+  B2N_GATE(g);
   if (dupes && *dupes > dupe_limit) return;  // clustered input: k_place_agg does the work
   const int lane = threadIdx.x & 31;
-  const int64_t c0 = (int64_t)blockIdx.x * (256 * PL_E);
+  int64_t c0 = (int64_t)blockIdx.x * (256 * PL_E);
+  if (PADDED) {
+    const int b = (int)(c0 / cap);
+    M = (int64_t)b * cap + bucket_cnt[b];
+  }
   for (int e0 = 0; e0 < PL_E; e0 += PL_G) {
     if (c0 + e0 * 256 + (threadIdx.x - lane) >= M) break;  // whole warp past the end
     PtRec<T> r[PL_G];
@@ -511,6 +549,7 @@ __global__ void __launch_bounds__(PA_T) k_place_agg(SortGeom g, int64_t M, const
                                                      PtRec<T> *__restrict__ out,
                                                      const int32_t *__restrict__ dupes, int64_t dupe_limit) {
   B2N_SKIP_IF(g.skip);
+  B2N_GATE(g);
   if (*dupes <= dupe_limit) return;
   extern __shared__ int pa_smem[];
   int *tkey = pa_smem, *tcnt = pa_smem + PA_HT;        // cnt doubles as the reserved base in phase 3
@@ -589,6 +628,14 @@ __global__ void __launch_bounds__(PA_T) k_place_agg(SortGeom g, int64_t M, const
       out[pos] = r;
     }
   }
+}
+
+// p[0 .. n) = 0 when *flag == want (the fallback of the two-pass sort starts from clean counters)
+__global__ void __launch_bounds__(256) k_zero_if(const int *flag, int want, int32_t *__restrict__ p, int64_t n,
+                                                  const int *skip) {
+  B2N_SKIP_IF(skip);
+  if (*flag != want) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = 0;
 }
 
 // gpu_sort = 0: identity permutation, folded coordinates only
@@ -738,6 +785,8 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   }
   for (int d = 0; d < 3; d++)
     g.magic[d] = g.bin[d] > 1 ? (unsigned)(((1ull << 32) + g.bin[d] - 1) / g.bin[d]) : 0u;
+  g.gate = nullptr;
+  g.gate_val = 0;
   g.nsub = ps.nsub = (p.method == 3 && p.dim == 3) ? p.bin[2] : 1;
   g.swr_ns = p.method == 3 ? p.ns : 0;
   // >= 1024 points per CTA: every CTA of the histogram pass sets up (and scans) its hot-key table
@@ -800,16 +849,48 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     ps.cap_bins = nbins;
   }
   if (!ps.bucket_cur)
-    if (int e = dev_alloc_t(&ps.bucket_cur, 256, st)) return e;
+    if (int e = dev_alloc_t(&ps.bucket_cur, 256 + 8, st)) return e;  // [256]: overflow flag of the two-pass sort
   const int64_t sp_cap = std::min<int64_t>(nbins, M) + M / p.maxsub + 1;
   if (int e = grow(&ps.sp_bin, &ps.cap_sp, sp_cap, st)) return e;
   ps.sp_cap = sp_cap;
 
-  // P0 + scan
   int32_t *dupes = ps.key_cnt + K;  // lanes merged by the histogram pass (clustering signal)
-  B2N_CUDA_OK(cudaMemsetAsync(ps.key_cnt, 0, sizeof(int32_t) * (K + 1), st));
   const int64_t dupe_limit = M / 8;
-  if (M > 0) k_key_hist<T><<<nblk, 256, 0, st>>>(g, M, x, y, z, ps.key_cnt, dupes);  B2N_LAUNCHED(1);
+  // bucket geometry: windows of ~4 MB of records, at most 256 buckets; one bucket = no P1
+  const int64_t bytes = M * (int64_t)sizeof(PtRec<T>);
+  int64_t want = bytes <= (48LL << 20) ? 1 : std::min<int64_t>(256, (bytes + (4LL << 20) - 1) / (4LL << 20));
+  int shift = 0;
+  while (((K - 1) >> shift) + 1 > want) shift++;
+  const int nbuckets = (int)(((K - 1) >> shift) + 1);
+  const int nplace = cdiv(std::max<int64_t>(M, 1), 256 * PL_E);
+  const size_t pa_smem = (2 * PA_HT + PA_N) * sizeof(int);
+  B2N_CUDA_OK(cudaFuncSetAttribute(k_place_agg<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pa_smem));
+  B2N_CUDA_OK(cudaFuncSetAttribute(k_place_agg<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pa_smem));
+  B2N_CUDA_OK(cudaMemsetAsync(ps.key_cnt, 0, sizeof(int32_t) * (K + 1), st));
+
+  // TWO-PASS SORT (large inputs): P1 partitions into fixed-capacity bucket regions and counts the
+  // keys as it goes; the scan and the subproblem list follow; P2 places.  A bucket that outgrows
+  // its region (strongly non-uniform input) raises a device flag: the passes of this path then
+  // return at once and the three-pass pipeline below runs instead -- all decided on the device.
+  static const bool no_fast = getenv("B2N_SORT_THREE_PASS") != nullptr;
+  const int64_t cap64 = (((int64_t)((double)M / nbuckets * 1.5) + 8192 + 2047) / 2048) * 2048;
+  const bool fast = !no_fast && nbuckets > 1 && cap64 * nbuckets < 0x7fffffffLL;
+  const int cap = (int)cap64;
+  int *ovf = ps.bucket_cur + 256;
+  SortGeom gslow = g, gfast = g;
+  if (fast) {
+    if (int e = grow(&ps.tmp, &ps.cap_tmp, cap64 * nbuckets, st)) return e;
+    B2N_CUDA_OK(cudaMemsetAsync(ps.bucket_cur, 0, sizeof(int32_t) * (256 + 8), st));
+    gfast.gate = ovf; gfast.gate_val = 0;
+    gslow.gate = ovf; gslow.gate_val = 1;
+    k_partition<T, true><<<cdiv(M, PT_T * PartCfg<T>::E), PT_T, 0, st>>>(gfast, M, x, y, z, nullptr, K, shift, nbuckets,
+                                                                       ps.bucket_cur, ps.tmp, cap, ps.key_cnt, ovf);
+    // overflow: clean counters for the fallback's histogram and partition
+    k_zero_if<<<148 * 4, 256, 0, st>>>(ovf, 1, ps.key_cnt, K + 1, g.skip);
+    B2N_LAUNCHED(2);
+    B2N_LAUNCH_OK();
+  }
+  if (M > 0) k_key_hist<T><<<nblk, 256, 0, st>>>(gslow, M, x, y, z, ps.key_cnt, dupes);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   if (int e = exclusive_scan_i32(ps.key_cnt, ps.key_start, K, st, g.skip)) return e;
 
@@ -827,24 +908,23 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
     B2N_LAUNCH_OK();
   }
 
-  // bucket geometry: windows of ~4 MB of records, at most 256 buckets; one bucket = no P1
-  const int64_t bytes = M * (int64_t)sizeof(PtRec<T>);
-  int64_t want = bytes <= (48LL << 20) ? 1 : std::min<int64_t>(256, (bytes + (4LL << 20) - 1) / (4LL << 20));
-  int shift = 0;
-  while (((K - 1) >> shift) + 1 > want) shift++;
-  const int nbuckets = (int)(((K - 1) >> shift) + 1);
   if (M > 0) {
-    const int nplace = cdiv(M, 256 * PL_E);
-    const size_t pa_smem = (2 * PA_HT + PA_N) * sizeof(int);
-    B2N_CUDA_OK(cudaFuncSetAttribute(k_place_agg<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pa_smem));
-    B2N_CUDA_OK(cudaFuncSetAttribute(k_place_agg<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pa_smem));
+    if (fast) {  // P2 of the two-pass sort: the padded bucket regions, bucket by bucket
+      k_place<T, false, true><<<(unsigned)(cap64 * nbuckets / (256 * PL_E)), 256, 0, st>>>(
+          gfast, M, x, y, z, ps.tmp, ps.key_start, ps.rec, nullptr, 0, cap, ps.bucket_cur);
+      // ... or, after an overflow, P1 + P2 of the three-pass pipeline (write cursors cleared first)
+      k_zero_if<<<1, 256, 0, st>>>(ovf, 1, ps.bucket_cur, 256, g.skip);
+      B2N_LAUNCHED(2);
+    }
     if (nbuckets > 1) {
-      if (int e = grow(&ps.tmp, &ps.cap_tmp, M, st)) return e;
-      B2N_CUDA_OK(cudaMemsetAsync(ps.bucket_cur, 0, sizeof(int32_t) * 256, st));
-      k_partition<T><<<cdiv(M, PT_T * PartCfg<T>::E), PT_T, 0, st>>>(g, M, x, y, z, ps.key_start, K, shift,
-                                                                   nbuckets, ps.bucket_cur, ps.tmp);
-      k_place<T, false><<<nplace, 256, 0, st>>>(g, M, x, y, z, ps.tmp, ps.key_start, ps.rec, dupes, dupe_limit);
-      k_place_agg<T, false><<<cdiv(M, PA_N), PA_T, pa_smem, st>>>(g, M, x, y, z, ps.tmp, ps.key_start, ps.rec, dupes, dupe_limit);
+      if (!fast) {
+        if (int e = grow(&ps.tmp, &ps.cap_tmp, M, st)) return e;
+        B2N_CUDA_OK(cudaMemsetAsync(ps.bucket_cur, 0, sizeof(int32_t) * 256, st));
+      }
+      k_partition<T, false><<<cdiv(M, PT_T * PartCfg<T>::E), PT_T, 0, st>>>(gslow, M, x, y, z, ps.key_start, K, shift,
+                                                                          nbuckets, ps.bucket_cur, ps.tmp, 0, nullptr, nullptr);
+      k_place<T, false><<<nplace, 256, 0, st>>>(gslow, M, x, y, z, ps.tmp, ps.key_start, ps.rec, dupes, dupe_limit);
+      k_place_agg<T, false><<<cdiv(M, PA_N), PA_T, pa_smem, st>>>(gslow, M, x, y, z, ps.tmp, ps.key_start, ps.rec, dupes, dupe_limit);
       B2N_LAUNCHED(3);
     } else {
       k_place<T, true><<<nplace, 256, 0, st>>>(g, M, x, y, z, nullptr, ps.key_start, ps.rec, dupes, dupe_limit);

@@ -449,3 +449,36 @@ def test_full_size_properties_c3(typ):
         truth = torch.einsum("jz,jz->j", t, ex[2])
         got = Cc[0][js].to(torch.complex128)
         assert float(torch.linalg.norm(got - truth) / torch.linalg.norm(truth)) < 2e-5
+
+
+@pytest.mark.parametrize("frac", [0.0, 0.5, 1.0], ids=["uniform", "half_clustered", "clustered"])
+def test_two_pass_sort_and_its_overflow_fallback(frac):
+    """Point sets large enough for the bucketed sort (> 48 MB of records).  Uniform input takes the
+    two-pass sort (fixed-capacity bucket regions, histogram taken while partitioning); a bucket that
+    outgrows its region flips a device flag MID-KERNEL and the three-pass pipeline takes over.  (The
+    first version let every thread read that flag on its own: threads of one CTA parted ways in front
+    of a barrier and wrote out of bounds -- only at full speed, never under the sanitizer.)"""
+    from jax_finufft_b200.plan import Plan
+
+    M, nm = 3_600_000, (64, 64, 64)
+    rng = np.random.default_rng(31)
+    k = int(M * frac)
+    pts = []
+    for d in range(3):
+        u = rng.uniform(-np.pi, np.pi, M).astype(np.float32)
+        u[:k] = (-np.pi + rng.uniform(0, 8 * 2 * np.pi / 128, k)).astype(np.float32)
+        pts.append(u)
+    perm = rng.permutation(M)
+    pts = [u[perm] for u in pts]
+    c = (rng.uniform(-1, 1, (1, M)) + 1j * rng.uniform(-1, 1, (1, M))).astype(np.complex64)
+    tp = [T(u) for u in pts]
+    for rep in range(3):   # the race needed several tries to show
+        p = Plan(1, nm, eps=1e-5, isign=1)
+        p.setpts(*tp)
+        f = p.execute(T(c)).cpu().numpy()
+        idx, bs = p.sort_arrays()
+        p.destroy()
+        assert int(bs[-1]) == M
+        assert torch.equal(torch.sort(idx.long())[0], torch.arange(M, device="cuda"))
+    fo = oracle.nufft1(nm, c, *[u.astype(np.float64) for u in pts], eps=1e-5, prec=1)
+    assert oracle.relerr(f, fo) < G.parity_tol(1e-5, False)
