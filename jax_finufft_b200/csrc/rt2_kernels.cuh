@@ -439,28 +439,53 @@ __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __gri
   const PtRec<float> *recp = a.rec + first + lane;
   const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
   // the 64 bytes of strengths of the point of record rc -> buffer `buf`, row `lane`
-  auto issue_str = [&](int buf, const float4 &rc, bool valid) {
+  auto issue_str = [&](int buf, const float4 &rc, bool valid, int prow) {
     if (valid) {
       const float2 *src = cpack + (int64_t)__float_as_int(rc.w) * NT;
-      const unsigned dst = sm0 + (C::CSO + (buf * C::PB + lane) * 2 * NT) * 4;
+      const unsigned dst = sm0 + (C::CSO + (buf * C::PB + prow) * 2 * NT) * 4;
 #pragma unroll
       for (int k = 0; k < NT / 2; k++)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * k), "l"(src + 2 * k) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // Row of a point inside its batch: class-major (the order inside a bin is free).  Class 0: the y
+  // window ends below row slot S-1, class 2: it starts above row slot 0, class 1: anything else --
+  // the loops of classes 0 and 2 do not issue the FFMA2s of the row slot they cannot touch (2 of 3
+  // per transform).  The order is fixed when the strengths of the batch are requested (one batch
+  // ahead, they land in the row of their point), so the loops below have warp-uniform trip counts.
+  auto order = [&](const float4 &rc, int n, int &pos, int &n0, int &n01) {
+    pos = lane; n0 = 0; n01 = n;
+    if constexpr (S == 3) {
+      const bool act = lane < n;
+      int yl = window_start(rc.y, NS) - ya;
+      yl = yl < 0 ? 0 : (yl > C::WY - NS ? C::WY - NS : yl);
+      const int cls = yl + NS <= 4 * (S - 1) ? 0 : (yl >= 4 ? 2 : 1);
+      const unsigned b0 = __ballot_sync(0xffffffffu, act && cls == 0);
+      const unsigned b1 = __ballot_sync(0xffffffffu, act && cls == 1);
+      const unsigned b2 = __ballot_sync(0xffffffffu, act && cls == 2);
+      const unsigned lt = (1u << lane) - 1u;
+      n0 = __popc(b0);
+      n01 = n0 + __popc(b1);
+      pos = cls == 0 ? __popc(b0 & lt) : (cls == 1 ? n0 + __popc(b1 & lt) : n01 + __popc(b2 & lt));
+    }
+  };
   float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
   float4 recB = lane + C::PB < cnt ? ld_stream4(recp + C::PB) : zrec;
-  issue_str(0, recA, lane < cnt);
+  int posA, n0A, n01A;
+  order(recA, min(C::PB, cnt), posA, n0A, n01A);
+  issue_str(0, recA, lane < cnt, posA);
   const unsigned ax = sm0 + (C::KXO + q) * 4, ay = sm0 + (C::KYO + 4 * r) * 4;
   int bi = 0;
   for (int b0 = 0; b0 < cnt; b0 += C::PB, bi++) {
     const int nb = min(C::PB, cnt - b0);
     const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
-    issue_str((bi + 1) & 1, recB, b0 + C::PB + lane < cnt);
+    int posB, n0B, n01B;
+    order(recB, max(0, min(C::PB, cnt - b0 - C::PB)), posB, n0B, n01B);
+    issue_str((bi + 1) & 1, recB, b0 + C::PB + lane < cnt, posB);
     __syncwarp();
     if (lane < nb) {  // kernel vectors of point b0 + lane, once for all transforms
-      float *row = rows + lane * C::ROW;
+      float *row = rows + posA * C::ROW;
       const float px = recA.x, py = recA.y;
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -510,26 +535,46 @@ __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __gri
     recA = recB;
     recB = recC;
     const unsigned cs = sm0 + (C::CSO + (bi & 1) * C::PB * 2 * NT) * 4;
+    // all transforms of the points [p0, p1) of this batch; per point 3 FMUL (kx * ky[s], shared by the
+    // transforms) and per transform one FFMA2 per row slot: acc += c_t * (kx ky[s]) with the strength
+    // pair as the vector operand and the weight as the scalar-broadcast one
+    auto run = [&](auto clc, int p0, int p1) {
+      constexpr int CLS = decltype(clc)::value;
+      constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
 #pragma unroll 2
-    for (int p = 0; p < nb; p++) {
-      float kxv;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(kxv) : "r"(ax + p * C::ROW * 4));
-      float4 ky4;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ky4.x), "=f"(ky4.y), "=f"(ky4.z), "=f"(ky4.w) : "r"(ay + p * C::ROW * 4));
-      const float2 kx2 = make_float2(kxv, kxv);
-      const float2 kys[4] = {make_float2(ky4.x, ky4.x), make_float2(ky4.y, ky4.y), make_float2(ky4.z, ky4.z), make_float2(ky4.w, ky4.w)};
+      for (int p = p0; p < p1; p++) {
+        float kxv;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(kxv) : "r"(ax + p * C::ROW * 4));
+        float4 ky4;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ky4.x), "=f"(ky4.y), "=f"(ky4.z), "=f"(ky4.w) : "r"(ay + p * C::ROW * 4));
+        const float kyv[4] = {ky4.x, ky4.y, ky4.z, ky4.w};
+        float2 kxy[S];
 #pragma unroll
-      for (int t = 0; t < NT; t += 2) {
-        float4 c2;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c2.x), "=f"(c2.y), "=f"(c2.z), "=f"(c2.w) : "r"(cs + (p * 2 * NT + 2 * t) * 4));
-        const float2 w0 = mul2(make_float2(c2.x, c2.y), kx2), w1 = mul2(make_float2(c2.z, c2.w), kx2);
+        for (int s = S0; s < S1; s++) {
+          const float w = kxv * kyv[s];
+          kxy[s] = make_float2(w, w);
+        }
 #pragma unroll
-        for (int s = 0; s < S; s++) {
-          acc[t][s] = fma2(w0, kys[s], acc[t][s]);
-          acc[t + 1][s] = fma2(w1, kys[s], acc[t + 1][s]);
+        for (int t = 0; t < NT; t += 2) {
+          float4 c2;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c2.x), "=f"(c2.y), "=f"(c2.z), "=f"(c2.w) : "r"(cs + (p * 2 * NT + 2 * t) * 4));
+          const float2 c0 = make_float2(c2.x, c2.y), c1 = make_float2(c2.z, c2.w);
+#pragma unroll
+          for (int s = S0; s < S1; s++) {
+            acc[t][s] = fma2(c0, kxy[s], acc[t][s]);
+            acc[t + 1][s] = fma2(c1, kxy[s], acc[t + 1][s]);
+          }
         }
       }
+    };
+    if constexpr (S == 3) {
+      run(std::integral_constant<int, 0>{}, 0, n0A);
+      run(std::integral_constant<int, 1>{}, n0A, n01A);
+      run(std::integral_constant<int, 2>{}, n01A, nb);
+    } else {
+      run(std::integral_constant<int, 1>{}, 0, nb);
     }
+    posA = posB; n0A = n0B; n01A = n01B;
     __syncwarp();
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");

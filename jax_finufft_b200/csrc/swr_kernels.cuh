@@ -462,12 +462,10 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
     constexpr int PH = decltype(phc)::value;
     constexpr int CLS = decltype(clc)::value;  // see swr_batch_order: the row slot a class never touches is skipped
     constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
-    float2 wv[S][CX];
-#pragma unroll
-    for (int s = S0; s < S1; s++)
-#pragma unroll
-      for (int c = 0; c < CX; c++) wv[s][c] = mul2(pr.cx[c], pr.kyv(s));
-    pr.load_xy(myx, myy, ron);
+    // value = kx * sum_s ky[s] * (sum_k plane[s][k] * kz[k]): the x and y weights enter AFTER the
+    // plane sums as scalar-broadcast operands (S FMUL2/FFMA2 + one FMUL2 per cell column) instead
+    // of as S precomputed (kx * ky[s]) pairs (S FMUL2 more per point, held across the FMA block),
+    // so their rolling load moves behind the final dot product.
     float2 part[S][CX];
 #pragma unroll
     for (int i = 0; i < SwrRow<NS>::NV; i++) {
@@ -485,12 +483,16 @@ __global__ void __launch_bounds__(32 * SwrCfg<NS>::WARPS, SwrCfg<NS>::MINB)
       }
       pr.load_kv(rows, ron, i);
     }
-    float2 res = mul2(part[S0][0], wv[S0][0]);
+    float2 res;
 #pragma unroll
-    for (int s = S0; s < S1; s++)
+    for (int c = 0; c < CX; c++) {
+      float2 pc = mul2(part[S0][c], pr.kyv(S0));
 #pragma unroll
-      for (int c = 0; c < CX; c++)
-        if (s - S0 + c > 0) res = fma2(part[s][c], wv[s][c], res);
+      for (int s = S0 + 1; s < S1; s++) pc = fma2(part[s][c], pr.kyv(s), pc);
+      const float2 kxc = make_float2(pr.cx[c].x, pr.cx[c].x);
+      res = c == 0 ? mul2(pc, kxc) : fma2(pc, kxc, res);
+    }
+    pr.load_xy(myx, myy, ron);
     return res;
   };
 
