@@ -105,6 +105,7 @@ template <typename T> Plan<T>::~Plan() {
   }
   dev_free(fw, st);
   dev_free(cpack, st);
+  dev_free(fw_stack, st);
   dev_free(pts.rec, st);
   dev_free(pts.tmp, st);
   dev_free(pts.idx, st);
@@ -550,7 +551,7 @@ template <typename T> static cufftResult fft_exec(cufftHandle h, cpx<T> *d, int 
 }
 
 // blk = transforms of the current batch that hold data
-template <typename T> static int run_fft(Plan<T> &p, int blk = -1) {
+template <typename T> static int run_fft(Plan<T> &p, int blk = -1, cpx<T> *grid = nullptr) {
   const int dir = p.iflag >= 0 ? CUFFT_INVERSE : CUFFT_FORWARD;  // cufft_ex(.., iflag): types.h:108-115
   if (p.pruned) {
     // type 1: the grid is full, only the mode planes of the result are read  -> z first, then
@@ -568,16 +569,60 @@ template <typename T> static int run_fft(Plan<T> &p, int blk = -1) {
     }
     return 0;
   }
-  cufftResult r;
-  if (sizeof(T) == 4) r = cufftExecC2C(p.fft, (cufftComplex *)p.fw, (cufftComplex *)p.fw, dir);
-  else r = cufftExecZ2Z(p.fft, (cufftDoubleComplex *)p.fw, (cufftDoubleComplex *)p.fw, dir);
-  return r == CUFFT_SUCCESS ? 0 : B2N_ERR_CUDA_FAILURE;
+  return fft_exec<T>(p.fft, grid ? grid : p.fw, dir) == CUFFT_SUCCESS ? 0 : B2N_ERR_CUDA_FAILURE;
+}
+
+// Stacked 2-D type 1 (jax-finufft's vmap stacking, BASELINE config 4) with more transforms than one
+// batch: the spreader takes a whole GROUP of batches in one launch (rt2_kernels.cuh: k_rt2s_spread
+// runs its passes of 8 transforms back to back, kernel vectors evaluated once), into a stack of
+// fine grids of its own; FFT and deconvolution then go through the stack batch by batch with the
+// plan's batched cuFFT handle.  The group is bounded by B2N_STACK_BYTES (default 8 GB) for the
+// stack plus the point-major copy of the strengths.
+template <typename T> int Plan<T>::exec1_stacked(cpx<T> *c, cpx<T> *fk, int group) {
+  const bool dbg = opts.debug != 0;
+  const int64_t M = pts.M;
+  const int64_t need = (int64_t)(group + batch) * nftot;  // + one batch: the cuFFT handle always runs `batch` grids
+  if (need > cap_fw_stack) {
+    dev_free(fw_stack, stream);
+    fw_stack = nullptr;
+    cap_fw_stack = 0;
+    if (int e = dev_alloc_t(&fw_stack, (size_t)need, stream)) return e;
+    cap_fw_stack = need;
+  }
+  for (int g0 = 0; g0 < ntransf; g0 += group) {
+    const int ng = std::min(group, ntransf - g0);
+    {
+      StageTimer tm(dbg, stream, &timings[6]);
+      const size_t nclear = (size_t)((ng + batch - 1) / batch * batch);  // whole batches: the FFT runs on the padding too
+      B2N_CUDA_OK(cudaMemsetAsync(fw_stack, 0, sizeof(cpx<T>) * nclear * (size_t)nftot, stream));
+    }
+    {
+      StageTimer tm(dbg, stream, &timings[1]);
+      if (int e = spread(c + (int64_t)g0 * M, nullptr, fw_stack, ng)) return e;
+    }
+    for (int b = 0; b < ng; b += batch) {
+      const int blk = std::min(batch, ng - b);
+      cpx<T> *grid = fw_stack + (int64_t)b * nftot;
+      {
+        StageTimer tm(dbg, stream, &timings[2]);
+        if (int e = run_fft(*this, blk, grid)) return e;
+      }
+      StageTimer tm(dbg, stream, &timings[3]);
+      if (int e = deconvolve<T>(*this, grid, fk + (int64_t)(g0 + b) * nmodes, blk)) return e;
+    }
+  }
+  return 0;
 }
 
 // Type 1: V/src/cuda/3d/cufinufft3d.cu:18-73 (and 1d/2d twins)
 template <typename T> int Plan<T>::exec1(cpx<T> *c, cpx<T> *fk) {
   const bool dbg = opts.debug != 0;
   const int64_t M = pts.M;
+  if (stacked2 && method == 3 && ntransf > batch && batch == 8 && !pruned) {
+    static const double budget = getenv("B2N_STACK_BYTES") ? atof(getenv("B2N_STACK_BYTES")) : 8e9;
+    const int64_t g = (int64_t)(budget / (sizeof(cpx<T>) * (double)(nftot + M))) / batch * batch;
+    if (g >= 2 * batch) return exec1_stacked(c, fk, (int)std::min<int64_t>(g, (ntransf + batch - 1) / batch * batch));
+  }
   for (int i = 0; i * batch < ntransf; i++) {
     const int blk = std::min(ntransf - i * batch, batch);
     cpx<T> *cs = c + (int64_t)i * batch * M;

@@ -137,6 +137,15 @@ __device__ __forceinline__ void eval_kernel_rt(T *ker, int ns, T x1, const Horne
 __device__ __forceinline__ void red_add(float2 *addr, float2 v) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
+// the same, skipped (predicated, no branch) when both parts are zero
+__device__ __forceinline__ void red_add_nz(float2 *addr, float2 v) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.neu.f32 p, %1, 0f00000000;\n\t"
+      "setp.neu.f32 q, %2, 0f00000000;\n\t"
+      "or.pred p, p, q;\n\t"
+      "@p red.global.add.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ void red_add4(float4 *addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)

@@ -94,8 +94,10 @@ template <typename T> struct Plan : PlanBase {
   int base_method = 0, base_bin[3] = {1, 1, 1}, base_maxsub = 1024;
   bool swr_ok = false;
   bool stacked2 = false;  // 2-D type 1 with stacked transforms: narrow-window bins (rt2_kernels.cuh, Rt2sCfg)
-  cpx<T> *cpack = nullptr;  // point-major strengths of one batch of transforms [M][8]
+  cpx<T> *cpack = nullptr;  // point-major strengths of the stacked transforms of one spread launch [M][8 * passes]
   int64_t cap_cpack = 0;
+  cpx<T> *fw_stack = nullptr;  // stacked 2-D type 1: fine grids of a whole GROUP of batches (exec1_stacked)
+  int64_t cap_fw_stack = 0;
   HornerTable<T> tab;
   cudaStream_t stream = 0;
   cudaStream_t side = nullptr;             // overlap_begin / overlap_join
@@ -143,6 +145,7 @@ template <typename T> struct Plan : PlanBase {
   int spread(const cpx<T> *c, const cpx<T> *prescale, cpx<T> *grid, int ntr);
   int interp(cpx<T> *c, const cpx<T> *postscale, const cpx<T> *grid, int ntr);
   int exec1(cpx<T> *c, cpx<T> *fk);
+  int exec1_stacked(cpx<T> *c, cpx<T> *fk, int group);
   int exec2(cpx<T> *c, cpx<T> *fk, const cpx<T> *postscale);
   int exec3(cpx<T> *c, cpx<T> *fk);
   void info(b2n_plan_info *out) override;

@@ -391,33 +391,55 @@ template <int NS> struct Rt2sCfg {
   static constexpr int H = NS / 2;
   static constexpr int BX = WX - NS + 1, BY = WY - NS + 1;
   static constexpr int PB = 32;
+  static constexpr int CB = 2;         // batches whose weight rows stay in shared memory across the passes
   static constexpr int NP = (NS + 1) / 2;
   static constexpr int KXO = 0;        // 8 x weights (zero outside the stencil)
   static constexpr int KYO = 8;        // ky[r = row & 3][row >> 2], 4 x 4 (3 used)
   static constexpr int ROW = 28;       // 24 floats + 4: stride / 4 odd
-  static constexpr int CSO = PB * ROW; // strengths: [2 buffers][PB points][NT complex]
+  static constexpr int CSO = CB * PB * ROW;  // strengths: [2 buffers][PB points][NT complex]
   static constexpr int SMEM = (CSO + 2 * PB * 2 * NT) * (int)sizeof(float);
   static_assert(BX >= 1 && BY >= 1, "window too small");
 };
 
-// cpack[i][t] = c[t][i], t < NT (zero beyond nt): a tiled transpose is not needed -- every thread
-// writes the 64 contiguous bytes of its point, a warp 2 KB
-template <int NT>
-__global__ void __launch_bounds__(256) k_pack_strengths(const float2 *__restrict__ c, int64_t M, int nt,
+// cpack[i][t] = c[t][i], t < cstride (zero beyond nt), cstride = NT * passes: a transpose of 32
+// points x (up to) 64 transforms per CTA through shared memory.  Reads are 256-byte runs of one
+// transform, writes the contiguous cstride * 8 bytes of each point (16 KB per CTA at 64
+// transforms).  Without the tile -- every thread writing the 64-byte pieces of its own point, 512
+// bytes apart from its neighbour's -- the pack ran at 3.4 TB/s instead of 6.5 (profiles/r02t).
+constexpr int PK_T = 64;  // transforms per tile
+__global__ void __launch_bounds__(256) k_pack_strengths(const float2 *__restrict__ c, int64_t M, int nt, int cstride,
                                                          float2 *__restrict__ cpack) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M) return;
-  float2 v[NT];
-#pragma unroll
-  for (int t = 0; t < NT; t++) v[t] = t < nt ? __ldcs(c + (int64_t)t * M + i) : make_float2(0.f, 0.f);
-  float4 *dst = reinterpret_cast<float4 *>(cpack + i * NT);
-#pragma unroll
-  for (int t = 0; t < NT; t += 2) dst[t / 2] = make_float4(v[t].x, v[t].y, v[t + 1].x, v[t + 1].y);
+  __shared__ float2 tile[32][PK_T + 1];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int np = (int)min((int64_t)32, M - i0);
+  for (int tc = 0; tc < cstride; tc += PK_T) {
+    const int tw = min(PK_T, cstride - tc);  // multiple of 8
+    if (tc) __syncthreads();
+    for (int t = w; t < tw; t += 8)
+      tile[lane][t] = (tc + t < nt && lane < np) ? __ldcs(c + (int64_t)(tc + t) * M + i0 + lane) : make_float2(0.f, 0.f);
+    __syncthreads();
+    const int h = tw / 2;  // float4 per point
+    for (int j = threadIdx.x; j < np * h; j += 256) {
+      const int p = j / h, e = j - p * h;
+      const float2 u = tile[p][2 * e], v = tile[p][2 * e + 1];
+      *reinterpret_cast<float4 *>(cpack + (i0 + p) * cstride + tc + 2 * e) = make_float4(u.x, u.y, v.x, v.y);
+    }
+  }
 }
 
+// One warp per subproblem, ALL nt stacked transforms of it, NT = 8 per pass.  A bin holds ~30
+// points at BASELINE config 4, so with one launch per 8 transforms a CTA lived ~8 us of which the
+// first 3 were the chain of dependent loads that finds its points (subproblem -> bin -> records ->
+// strengths; 26 % of all stall samples sat on the kernel's first instructions, profiles/r02t) and
+// the kernel vectors were re-evaluated for every group of 8.  Here the passes run back to back in
+// the same warp as one software pipeline over (pass, batch) steps: the strengths of the next step
+// are in flight (cp.async) while this one is spread, the weight rows of the first CB batches are
+// evaluated once and stay in shared memory, and the 24 accumulators are flushed to the pass's 8
+// fine grids at the end of each pass.
 template <int NS>
 __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __grid_constant__ HornerTable<float> tab,
-                                                     const float2 *__restrict__ cpack, int nt) {
+                                                     const float2 *__restrict__ cpack, int nt, int cstride) {
   using C = Rt2sCfg<NS>;
   constexpr int S = C::S, NP = C::NP, NT = C::NT;
   extern __shared__ __align__(16) float swr_smem[];
@@ -429,6 +451,8 @@ __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __gri
   const int r = lane >> 3, q = lane & 7;
   const int xa = x0 - C::H, ya = y0 - C::H;
   const int nf0 = a.nf[0], nf1 = a.nf[1];
+  const int nbat = (cnt + C::PB - 1) / C::PB, npass = (nt + NT - 1) / NT;
+  const bool cached = nbat <= C::CB;
 
   float2 acc[NT][S];
 #pragma unroll
@@ -438,10 +462,14 @@ __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __gri
 
   const PtRec<float> *recp = a.rec + first + lane;
   const float4 zrec = make_float4(0.f, 0.f, 0.f, 0.f);
-  // the 64 bytes of strengths of the point of record rc -> buffer `buf`, row `lane`
-  auto issue_str = [&](int buf, const float4 &rc, bool valid, int prow) {
+  // the 64 bytes of strengths (pass `ps`) of the point of record rc -> buffer `buf`, row `prow`
+  auto issue_str = [&](int buf, const float4 &rc, bool valid, int prow, int ps) {
     if (valid) {
-      const float2 *src = cpack + (int64_t)__float_as_int(rc.w) * NT;
+#ifdef RT2S_NO_GATHER  // experiment: strengths from one hot row instead of through idx
+      const float2 *src = cpack + (int64_t)(lane) * cstride + ps * NT;
+#else
+      const float2 *src = cpack + (int64_t)__float_as_int(rc.w) * cstride + ps * NT;
+#endif
       const unsigned dst = sm0 + (C::CSO + (buf * C::PB + prow) * 2 * NT) * 4;
 #pragma unroll
       for (int k = 0; k < NT / 2; k++)
@@ -452,7 +480,7 @@ __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __gri
   // Row of a point inside its batch: class-major (the order inside a bin is free).  Class 0: the y
   // window ends below row slot S-1, class 2: it starts above row slot 0, class 1: anything else --
   // the loops of classes 0 and 2 do not issue the FFMA2s of the row slot they cannot touch (2 of 3
-  // per transform).  The order is fixed when the strengths of the batch are requested (one batch
+  // per transform).  The order is fixed when the strengths of the step are requested (one step
   // ahead, they land in the row of their point), so the loops below have warp-uniform trip counts.
   auto order = [&](const float4 &rc, int n, int &pos, int &n0, int &n01) {
     pos = lane; n0 = 0; n01 = n;
@@ -470,22 +498,38 @@ __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __gri
       pos = cls == 0 ? __popc(b0 & lt) : (cls == 1 ? n0 + __popc(b1 & lt) : n01 + __popc(b2 & lt));
     }
   };
-  float4 recA = lane < cnt ? ld_stream4(recp) : zrec;
-  float4 recB = lane + C::PB < cnt ? ld_stream4(recp + C::PB) : zrec;
+  // this lane's cell of row slot s in the first fine grid; + t * nftot per transform
+  float2 *cell[S];
+  {
+    const int gx = wrap_once(xa + q, nf0);
+#pragma unroll
+    for (int s = 0; s < S; s++) cell[s] = a.fw + (int64_t)wrap_once(ya + 4 * s + r, nf1) * nf0 + gx;
+  }
+  // steps k = pass * nbat + batch; (bA, pA) = this step, (bB, pB) the next, (bC, pC) the one after
+  auto next_step = [&](int &b, int &ps) { if (++b == nbat) { b = 0; ps++; } };
+  auto rec_of = [&](int b, int ps) { return ps < npass && b * C::PB + lane < cnt ? ld_stream4(recp + b * C::PB) : zrec; };
+  auto count_of = [&](int b, int ps) { return ps < npass ? min(C::PB, cnt - b * C::PB) : 0; };
+  int bA = 0, pA = 0, bB = 0, pB = 0;
+  next_step(bB, pB);
+  int bC = bB, pC = pB;
+  next_step(bC, pC);
+  float4 recA = rec_of(bA, pA);
+  float4 recB = rec_of(bB, pB);
   int posA, n0A, n01A;
-  order(recA, min(C::PB, cnt), posA, n0A, n01A);
-  issue_str(0, recA, lane < cnt, posA);
+  order(recA, count_of(bA, pA), posA, n0A, n01A);
+  issue_str(0, recA, lane < cnt, posA, 0);
   const unsigned ax = sm0 + (C::KXO + q) * 4, ay = sm0 + (C::KYO + 4 * r) * 4;
-  int bi = 0;
-  for (int b0 = 0; b0 < cnt; b0 += C::PB, bi++) {
-    const int nb = min(C::PB, cnt - b0);
-    const float4 recC = b0 + 2 * C::PB + lane < cnt ? ld_stream4(recp + b0 + 2 * C::PB) : zrec;
+  for (int k = 0; pA < npass; k++) {
+    const int nb = count_of(bA, pA);
+    const float4 recC = rec_of(bC, pC);
     int posB, n0B, n01B;
-    order(recB, max(0, min(C::PB, cnt - b0 - C::PB)), posB, n0B, n01B);
-    issue_str((bi + 1) & 1, recB, b0 + C::PB + lane < cnt, posB);
+    const int nbB = count_of(bB, pB);
+    order(recB, nbB, posB, n0B, n01B);
+    issue_str((k + 1) & 1, recB, lane < nbB, posB, pB);
+    const int rbase = cached ? bA * C::PB : 0;  // first row of this batch
     __syncwarp();
-    if (lane < nb) {  // kernel vectors of point b0 + lane, once for all transforms
-      float *row = rows + posA * C::ROW;
+    if (lane < nb && (pA == 0 || !cached)) {  // kernel vectors of the point, once for all transforms
+      float *row = rows + (rbase + posA) * C::ROW;
       const float px = recA.x, py = recA.y;
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -499,10 +543,10 @@ __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __gri
         float2 ax2[NP], ay2[NP];
 #pragma unroll
         for (int j = 0; j < NP; j++) ax2[j] = ay2[j] = make_float2(tab.c[0][2 * j], tab.c[0][2 * j + 1]);
-        for (int k = 1; k < tab.ncoef; k++) {
+        for (int kk = 1; kk < tab.ncoef; kk++) {
 #pragma unroll
           for (int j = 0; j < NP; j++) {
-            const float2 cj = make_float2(tab.c[k][2 * j], tab.c[k][2 * j + 1]);
+            const float2 cj = make_float2(tab.c[kk][2 * j], tab.c[kk][2 * j + 1]);
             ax2[j] = fma2(ax2[j], zx2, cj);
             ay2[j] = fma2(ay2[j], zy2, cj);
           }
@@ -530,41 +574,59 @@ __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __gri
         row[C::KYO + 4 * (iy & 3) + (iy >> 2)] = ky[j];
       }
     }
-    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this batch's strengths have landed
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this step's strengths have landed
     __syncwarp();
-    recA = recB;
-    recB = recC;
-    const unsigned cs = sm0 + (C::CSO + (bi & 1) * C::PB * 2 * NT) * 4;
-    // all transforms of the points [p0, p1) of this batch; per point 3 FMUL (kx * ky[s], shared by the
-    // transforms) and per transform one FFMA2 per row slot: acc += c_t * (kx ky[s]) with the strength
-    // pair as the vector operand and the weight as the scalar-broadcast one
-    auto run = [&](auto clc, int p0, int p1) {
+    const unsigned cs = sm0 + (C::CSO + (k & 1) * C::PB * 2 * NT) * 4;
+    const unsigned axb = ax + rbase * C::ROW * 4, ayb = ay + rbase * C::ROW * 4;
+    // all NT transforms of the points [p0, p1) of this batch; per point S FMUL (kx * ky[s], shared by
+    // the transforms) and per transform one FFMA2 per row slot: acc += c_t * (kx ky[s]) with the
+    // strength pair as the vector operand and the weight as the scalar-broadcast one.  The operands
+    // of the NEXT point (rows are consecutive across the class loops) are loaded while this one is
+    // spread: at 4 warps per scheduler nothing else covers the shared-memory latency
+    // (short-scoreboard stalls 2.4 per issue without it, profiles/r02t).
+    struct Pt { float kx; float4 ky; float4 c[NT / 2]; };
+    auto load_pt = [&](Pt &d, int p) {
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d.kx) : "r"(axb + p * C::ROW * 4));
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d.ky.x), "=f"(d.ky.y), "=f"(d.ky.z), "=f"(d.ky.w) : "r"(ayb + p * C::ROW * 4));
+#pragma unroll
+      for (int t = 0; t < NT / 2; t++)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(d.c[t].x), "=f"(d.c[t].y), "=f"(d.c[t].z), "=f"(d.c[t].w) : "r"(cs + (p * 2 * NT + 4 * t) * 4));
+    };
+    Pt pa, pb;  // pa = the next point to spread when a loop is entered
+    load_pt(pa, 0);
+    auto spread_pt = [&](auto clc, const Pt &cur) {
       constexpr int CLS = decltype(clc)::value;
       constexpr int S0 = CLS == 2 ? 1 : 0, S1 = CLS == 0 ? S - 1 : S;
-#pragma unroll 2
-      for (int p = p0; p < p1; p++) {
-        float kxv;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(kxv) : "r"(ax + p * C::ROW * 4));
-        float4 ky4;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ky4.x), "=f"(ky4.y), "=f"(ky4.z), "=f"(ky4.w) : "r"(ay + p * C::ROW * 4));
-        const float kyv[4] = {ky4.x, ky4.y, ky4.z, ky4.w};
-        float2 kxy[S];
+      const float kyv[4] = {cur.ky.x, cur.ky.y, cur.ky.z, cur.ky.w};
+      float2 kxy[S];
+#pragma unroll
+      for (int s = S0; s < S1; s++) {
+        const float w = cur.kx * kyv[s];
+        kxy[s] = make_float2(w, w);
+      }
+#pragma unroll
+      for (int t = 0; t < NT; t += 2) {
+        const float2 c0 = make_float2(cur.c[t / 2].x, cur.c[t / 2].y), c1 = make_float2(cur.c[t / 2].z, cur.c[t / 2].w);
 #pragma unroll
         for (int s = S0; s < S1; s++) {
-          const float w = kxv * kyv[s];
-          kxy[s] = make_float2(w, w);
+          acc[t][s] = fma2(c0, kxy[s], acc[t][s]);
+          acc[t + 1][s] = fma2(c1, kxy[s], acc[t + 1][s]);
         }
-#pragma unroll
-        for (int t = 0; t < NT; t += 2) {
-          float4 c2;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(c2.x), "=f"(c2.y), "=f"(c2.z), "=f"(c2.w) : "r"(cs + (p * 2 * NT + 2 * t) * 4));
-          const float2 c0 = make_float2(c2.x, c2.y), c1 = make_float2(c2.z, c2.w);
-#pragma unroll
-          for (int s = S0; s < S1; s++) {
-            acc[t][s] = fma2(c0, kxy[s], acc[t][s]);
-            acc[t + 1][s] = fma2(c1, kxy[s], acc[t + 1][s]);
-          }
-        }
+      }
+    };
+    auto run = [&](auto clc, int p0, int p1) {  // two points per trip: the register sets swap roles, no copies
+      int p = p0;
+#pragma unroll 1
+      for (; p + 1 < p1; p += 2) {
+        load_pt(pb, p + 1);
+        spread_pt(clc, pa);
+        load_pt(pa, min(p + 2, C::PB - 1));
+        spread_pt(clc, pb);
+      }
+      if (p < p1) {
+        load_pt(pb, min(p + 1, C::PB - 1));
+        spread_pt(clc, pa);
+        pa = pb;
       }
     };
     if constexpr (S == 3) {
@@ -574,21 +636,31 @@ __global__ void __launch_bounds__(32) k_rt2s_spread(const SwrArgs a, const __gri
     } else {
       run(std::integral_constant<int, 1>{}, 0, nb);
     }
-    posA = posB; n0A = n0B; n01A = n01B;
+    if (bA == nbat - 1) {  // end of pass pA: its NT fine grids take the window
+      const int tn = min(NT, nt - pA * NT);
+      const int64_t g0 = (int64_t)pA * NT * a.nftot;
+#pragma unroll
+      for (int t = 0; t < NT; t++) {
+        if (t < tn) {
+#pragma unroll
+          for (int s = 0; s < S; s++)
+#ifdef RT2S_NO_RED   // experiment: how much of the kernel is the flush
+            if (acc[t][s].x == 12345.f) red_add_nz(cell[s] + g0 + (int64_t)t * a.nftot, acc[t][s]);
+#else
+            red_add_nz(cell[s] + g0 + (int64_t)t * a.nftot, acc[t][s]);
+#endif
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) acc[t][s] = make_float2(0.f, 0.f);
+      }
+    }
     __syncwarp();
+    recA = recB; recB = recC;
+    posA = posB; n0A = n0B; n01A = n01B;
+    bA = bB; pA = pB; bB = bC; pB = pC;
+    next_step(bC, pC);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-  const int gx = wrap_once(xa + q, nf0);
-#pragma unroll
-  for (int t = 0; t < NT; t++) {
-    if (t >= nt) break;
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-      const int gy = wrap_once(ya + 4 * s + r, nf1);
-      if (acc[t][s].x != 0.f || acc[t][s].y != 0.f)
-        red_add(a.fw + (int64_t)t * a.nftot + (int64_t)gy * nf0 + gx, acc[t][s]);
-    }
-  }
 }
 
 // ==================================================================================== INTERP

@@ -134,22 +134,19 @@ template <int NS> static int rt2s_spread(Plan<float> &p, const SwrArgs &a, const
   if (p.ns == NS) {
     using C = Rt2sCfg<NS>;
     const int64_t M = p.pts.M;
-    if (M > p.cap_cpack) {
+    const int npass = (ntr + C::NT - 1) / C::NT, cstride = npass * C::NT;
+    if (M * cstride > p.cap_cpack) {
       dev_free(p.cpack, p.stream);
       p.cpack = nullptr;
       p.cap_cpack = 0;
-      if (int e = dev_alloc_t(&p.cpack, (size_t)M * C::NT, p.stream)) return e;
-      p.cap_cpack = M;
+      if (int e = dev_alloc_t(&p.cpack, (size_t)M * cstride, p.stream)) return e;
+      p.cap_cpack = M * cstride;
     }
     B2N_CUDA_OK(cudaFuncSetAttribute(k_rt2s_spread<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    for (int t0 = 0; t0 < ntr; t0 += C::NT) {  // ntr <= batch <= 8 by default: one pass
-      const int nt = std::min(C::NT, ntr - t0);
-      SwrArgs b = a;
-      b.fw = a.fw + (int64_t)t0 * a.nftot;
-      k_pack_strengths<C::NT><<<cdiv(M, 256), 256, 0, p.stream>>>(c + (int64_t)t0 * M, M, nt, p.cpack);
-      k_rt2s_spread<NS><<<(unsigned)p.pts.sp_cap, 32, C::SMEM, p.stream>>>(b, p.tab, p.cpack, nt);
-      B2N_LAUNCHED(2);
-    }
+    // all ntr transforms in one launch: the kernel runs its passes of NT back to back
+    k_pack_strengths<<<(unsigned)cdiv(M, 32), 256, 0, p.stream>>>(c, M, ntr, cstride, p.cpack);
+    k_rt2s_spread<NS><<<(unsigned)p.pts.sp_cap, 32, C::SMEM, p.stream>>>(a, p.tab, p.cpack, ntr, cstride);
+    B2N_LAUNCHED(2);
     B2N_LAUNCH_OK();
     return 0;
   }

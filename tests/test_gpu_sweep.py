@@ -102,6 +102,21 @@ def test_stacked_2d_type1_narrow_window_all_widths(eps, ntr):
         assert err < G.parity_tol(eps, False), (eps, ntr, t, err)
 
 
+@pytest.mark.parametrize("nm,M", [((128, 96), 120000), ((128, 96), 40000), ((44, 30), 40000)],
+                         ids=["bins_of_1_2_batches", "sparse_bins", "bins_of_3_batches"])
+@pytest.mark.parametrize("ntr", [16, 19])
+def test_stacked_2d_type1_groups_of_batches(nm, M, ntr):
+    """More stacked transforms than one batch (8): one spread launch takes the whole group and runs
+    its passes back to back (api.cu:exec1_stacked, k_rt2s_spread).  Bins of <= 64 points keep their
+    weight rows in shared memory across the passes, larger ones re-evaluate them; 19 = two full
+    passes and a partial one.  Every transform is checked against the oracle."""
+    out, want, info = _run(1, nm, M, 1e-6, ntr, 1, 0, 900 + ntr + M % 7, seam=True)
+    assert info.method == 3
+    worst = max(oracle.relerr(out[t], want[t]) for t in range(ntr))
+    print(f"\nPARITY stacked groups {nm} M={M} ntr={ntr}: worst {worst:.3e}")
+    assert worst < G.parity_tol(1e-6, False), worst
+
+
 @pytest.mark.parametrize("typ", [1, 2])
 @pytest.mark.parametrize("nm", [(40, 36), (40, 36, 32)])
 def test_register_kernels_low_upsampling(nm, typ):
