@@ -372,7 +372,10 @@ __global__ void __launch_bounds__(256) k_key_hist(SortGeom g, int64_t M, const T
 //   C  dest = off[bucket] + rank: perm[dest] = slot, pbkt[dest] = bucket
 //   D  thread t writes output positions t, t + T, ...: tmp[base[b] + j - off[b]] = smem[perm[j]]
 constexpr int PT_T = 256;
-template <typename T> struct PartCfg { static constexpr int E = sizeof(T) == 4 ? 8 : 4; };
+#ifndef PT_E
+#define PT_E 8  // records per thread (float): 2048 per CTA; 4 -> , 6 -> (A/B knob, profiles/r02v)
+#endif
+template <typename T> struct PartCfg { static constexpr int E = sizeof(T) == 4 ? PT_E : 4; };
 
 // FAST (two-pass sort): there is no histogram yet.  Bucket b owns the fixed region [b * cap,
 // (b + 1) * cap) of tmp; a run that does not fit raises *ovf (every later CTA then returns at once

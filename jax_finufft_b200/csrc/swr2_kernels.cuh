@@ -41,6 +41,9 @@ namespace b2n {
 #ifndef SWR2_PF
 #define SWR2_PF 3   // L2 prefetch distance of the register look-ahead variant
 #endif
+#ifndef SWR2_RETIRE_BRANCH
+#define SWR2_RETIRE_BRANCH 0
+#endif
 #ifndef SWR2_YCLASS_INTERP
 #define SWR2_YCLASS_INTERP 1
 #endif
@@ -328,10 +331,23 @@ __global__ void __launch_bounds__(32, Swr2Cfg<NS>::MINB2)
       case 6: one(std::integral_constant<int, 6>{}); break;
       default: one(std::integral_constant<int, 7>{}); break;
     }
+#if SWR2_RETIRE_BRANCH
+    // the periodic wrap is one plane in nf2: a branch (never taken in the common case) instead of
+    // the selects that built the step for every retired plane
+    if (++gz == nf2) {
+      gz = 0;
+#pragma unroll
+      for (int s = 0; s < S; s++) pz[s] -= (int64_t)(nf2 - 1) * pstride;
+    } else {
+#pragma unroll
+      for (int s = 0; s < S; s++) pz[s] += pstride;
+    }
+#else
     const int64_t step = gz + 1 == nf2 ? -(int64_t)(nf2 - 1) * pstride : pstride;
     gz = gz + 1 == nf2 ? 0 : gz + 1;
 #pragma unroll
     for (int s = 0; s < S; s++) pz[s] += step;
+#endif
   };
 
   Swr2Row<NS> pr;
