@@ -412,13 +412,28 @@ __global__ void __launch_bounds__(PT_T) k_partition(SortGeom g, int64_t M, const
   const int64_t c0 = (int64_t)blockIdx.x * N;
   const int nloc = (int)min((int64_t)N, M - c0);
   int br[E];  // bucket << 16 | rank inside (CTA, bucket)
+  // all of the thread's coordinates are requested BEFORE the first one is used: behind the atomics
+  // below the compiler kept each point's loads next to their use -- E dependent DRAM round trips
+  // per thread, 64 % of all stall samples on the first FFMA of every fold (profiles/r02v sortprof)
+  T cx[E], cy[E], cz[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    const int sl = e * PT_T + threadIdx.x;
+    cx[e] = cy[e] = cz[e] = T(0);
+    if (sl < nloc) {
+      cx[e] = x[c0 + sl];
+      if (g.dim > 1) cy[e] = y[c0 + sl];
+      if (g.dim > 2) cz[e] = z[c0 + sl];
+    }
+  }
 #pragma unroll
   for (int e = 0; e < E; e++) {
     const int sl = e * PT_T + threadIdx.x;
     br[e] = -1;
     if (sl < nloc) {
-      T xr, yr, zr;
-      fold3(g, c0 + sl, x, y, z, xr, yr, zr);
+      T xr = fold_rescale(cx[e], g.nf[0]);
+      T yr = g.dim > 1 ? fold_rescale(cy[e], g.nf[1]) : T(0);
+      T zr = g.dim > 2 ? fold_rescale(cz[e], g.nf[2]) : T(0);
       const int key = point_key(g, xr, yr, zr);
       if (FAST) atomicAdd(&hist[key], 1);
       const int bkt = key >> shift;
@@ -482,7 +497,12 @@ constexpr int PL_G = 8;  // points per thread in flight (4: 1.64 ms, 8: 1.44 ms,
 constexpr int PL_E = 8;  // points per thread; consecutive chunks per CTA keep the L2 window small
 // PADDED (two-pass sort): tmp holds bucket b in [b * cap, b * cap + bucket_cnt[b]); a CTA's 2048 slots lie
 // inside one bucket (cap is a multiple of 2048), M = end of that bucket's records.
-template <typename T, bool RAW, bool PADDED = false>
+// AGG = false: no search for equal keys inside the warp (MATCH.ANY + the shuffle of the leader's
+// base: 41 % of this kernel's stall samples were short-scoreboard waits on the match results).
+// Only the two-pass sort with many buckets uses it: there a cluster heavy enough to put equal keys
+// into one warp overflows its bucket region first and the three-pass pipeline (which aggregates)
+// takes over, so every key of a warp is almost surely distinct and aggregation buys nothing.
+template <typename T, bool RAW, bool PADDED = false, bool AGG = true>
 __global__ void __launch_bounds__(256) k_place(SortGeom g, int64_t M, const T *__restrict__ x,
                                                 const T *__restrict__ y, const T *__restrict__ z,
                                                 const PtRec<T> *__restrict__ tmp,
@@ -521,18 +541,26 @@ __global__ void __launch_bounds__(256) k_place(SortGeom g, int64_t M, const T *_
       const int64_t i = c0 + (e0 + u) * 256 + threadIdx.x;
       key[u] = i < M ? point_key(g, r[u].x, r[u].y, r[u].z) : -1 - lane;  // dummy keys are unique
     }
+    if constexpr (!AGG) {
 #pragma unroll
-    for (int u = 0; u < PL_G; u++) {
-      const unsigned peers = __match_any_sync(0xffffffffu, key[u]);
-      const int leader = __ffs(peers) - 1;
-      base[u] = 0;
-      if (key[u] >= 0 && lane == leader) base[u] = atomicAdd(&key_cursor[key[u]], __popc(peers));
-      lr[u] = leader | (__popc(peers & ((1u << lane) - 1u)) << 8);
-    }
+      for (int u = 0; u < PL_G; u++) base[u] = key[u] >= 0 ? atomicAdd(&key_cursor[key[u]], 1) : 0;
 #pragma unroll
-    for (int u = 0; u < PL_G; u++) {
-      const int b = __shfl_sync(0xffffffffu, base[u], lr[u] & 0xff);
-      if (key[u] >= 0) out[b + (lr[u] >> 8)] = r[u];
+      for (int u = 0; u < PL_G; u++)
+        if (key[u] >= 0) out[base[u]] = r[u];
+    } else {
+#pragma unroll
+      for (int u = 0; u < PL_G; u++) {
+        const unsigned peers = __match_any_sync(0xffffffffu, key[u]);
+        const int leader = __ffs(peers) - 1;
+        base[u] = 0;
+        if (key[u] >= 0 && lane == leader) base[u] = atomicAdd(&key_cursor[key[u]], __popc(peers));
+        lr[u] = leader | (__popc(peers & ((1u << lane) - 1u)) << 8);
+      }
+#pragma unroll
+      for (int u = 0; u < PL_G; u++) {
+        const int b = __shfl_sync(0xffffffffu, base[u], lr[u] & 0xff);
+        if (key[u] >= 0) out[b + (lr[u] >> 8)] = r[u];
+      }
     }
   }
 }
@@ -913,8 +941,12 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
 
   if (M > 0) {
     if (fast) {  // P2 of the two-pass sort: the padded bucket regions, bucket by bucket
-      k_place<T, false, true><<<(unsigned)(cap64 * nbuckets / (256 * PL_E)), 256, 0, st>>>(
-          gfast, M, x, y, z, ps.tmp, ps.key_start, ps.rec, nullptr, 0, cap, ps.bucket_cur);
+      if (nbuckets >= 64)
+        k_place<T, false, true, false><<<(unsigned)(cap64 * nbuckets / (256 * PL_E)), 256, 0, st>>>(
+            gfast, M, x, y, z, ps.tmp, ps.key_start, ps.rec, nullptr, 0, cap, ps.bucket_cur);
+      else
+        k_place<T, false, true, true><<<(unsigned)(cap64 * nbuckets / (256 * PL_E)), 256, 0, st>>>(
+            gfast, M, x, y, z, ps.tmp, ps.key_start, ps.rec, nullptr, 0, cap, ps.bucket_cur);
       // ... or, after an overflow, P1 + P2 of the three-pass pipeline (write cursors cleared first)
       k_zero_if<<<1, 256, 0, st>>>(ovf, 1, ps.bucket_cur, 256, g.skip);
       B2N_LAUNCHED(2);

@@ -17,8 +17,9 @@
  * Parity pinning: the reference stores no golden vectors; every reference
  * test checks against an on-the-fly direct NUDFT with fixed seeds.  This oracle is pinned the
  * same way (tests/test_oracle.py: seeds/sizes/tolerances of tests/ops_test.py:25-126 and
- * V/test/cuda/cufinufft3d_test.cu:186-254) and, on the GPU box, against the reference
- * cuFINUFFT library itself built into oracle/_ref (tests/test_ref_parity.py).
+ * V/test/cuda/cufinufft3d_test.cu:186-254), against outputs of the unmodified reference cuFINUFFT
+ * committed as tests/golden/ref_cufinufft_golden.npz (tests/test_oracle.py), and, on the GPU box,
+ * against the live library built into oracle/_ref (tests/test_gpu_fullsize_vs_reference.py).
  */
 #include <math.h>
 #include <stdint.h>
