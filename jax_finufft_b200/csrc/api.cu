@@ -435,6 +435,9 @@ int Plan<T>::setpts3(int64_t M, const T *x, const T *y, const T *z, int64_t N, c
       return e;
     }
   }
+  // the rescaled targets |s'| <= pi / sigma fill the central 1 / sigma of the inner grid's axes
+  // (impl.h:700-712: s' = h gamma (s - D), gamma = nf / (2 sigma S))
+  inner->sort_fill = 1.0 / inner->sigma;
   return inner->setpts12(N, sp[0], sp[1], sp[2]);
 }
 

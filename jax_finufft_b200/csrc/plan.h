@@ -93,6 +93,7 @@ template <typename T> struct Plan : PlanBase {
   // register kernels may take over once the point count is known (set_geometry, at setpts)
   int base_method = 0, base_bin[3] = {1, 1, 1}, base_maxsub = 1024;
   bool swr_ok = false;
+  double sort_fill = 1.0;  // fraction of the slowest axis the points are known to occupy (binsort_points: bucket capacity)
   bool stacked2 = false;  // 2-D type 1 with stacked transforms: narrow-window bins (rt2_kernels.cuh, Rt2sCfg)
   cpx<T> *cpack = nullptr;  // point-major strengths of the stacked transforms of one spread launch [M][8 * passes]
   int64_t cap_cpack = 0;

@@ -904,7 +904,11 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   // its region (strongly non-uniform input) raises a device flag: the passes of this path then
   // return at once and the three-pass pipeline below runs instead -- all decided on the device.
   static const bool no_fast = getenv("B2N_SORT_THREE_PASS") != nullptr;
-  const int64_t cap64 = (((int64_t)((double)M / nbuckets * 1.5) + 8192 + 2047) / 2048) * 2048;
+  // p.sort_fill < 1: the caller knows that the points fill only that fraction of the slowest axis
+  // (type-3 targets sit in the central 1/sigma of the inner grid), i.e. the occupied buckets hold
+  // 1/fill times the mean -- without the hint such a set always overflows and pays both pipelines
+  const double fill = std::min(1.0, std::max(0.1, p.sort_fill));
+  const int64_t cap64 = (((int64_t)((double)M / nbuckets / fill * 1.5) + 8192 + 2047) / 2048) * 2048;
   const bool fast = !no_fast && nbuckets > 1 && cap64 * nbuckets < 0x7fffffffLL;
   const int cap = (int)cap64;
   int *ovf = ps.bucket_cur + 256;

@@ -132,9 +132,9 @@ template <typename T> int deconvolve(Plan<T> &p, const cpx<T> *fw, cpx<T> *fk, i
 // with 32-bit arithmetic, three rows out of four (3-D) are pure zero fill, and every thread
 // stores two adjacent cells as one 16-byte word.  (The first version decoded each cell with
 // 64-bit divisions: 0.60 ms for 1.15 GB at C3, issue-bound at 29 % of the HBM roofline.)
-constexpr int AMP_T = 256;
+constexpr int AMP_T = 256, AMP_TMAX = 512;
 template <typename T>
-__global__ void __launch_bounds__(AMP_T) k_amplify(const ModeGeom g, cpx<T> *__restrict__ fw,
+__global__ void __launch_bounds__(AMP_TMAX) k_amplify(const ModeGeom g, cpx<T> *__restrict__ fw,
                                                     const cpx<T> *__restrict__ fk,
                                                     const T *__restrict__ h1, const T *__restrict__ h2,
                                                     const T *__restrict__ h3, int64_t nmodes,
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(AMP_T) k_amplify(const ModeGeom g, cpx<T> *__r
       rowok = k3 >= 0;
     }
   }
-  const int w1 = xc * (2 * AMP_T) + 2 * threadIdx.x;  // nf[0] is even for every grid the library builds
+  const int w1 = xc * (2 * (int)blockDim.x) + 2 * threadIdx.x;  // nf[0] is even for every grid the library builds
   if (w1 >= g.nf[0]) return;
   cpx<T> o[2];
   o[0].x = o[0].y = o[1].x = o[1].y = T(0);
@@ -188,11 +188,18 @@ template <typename T> int amplify(Plan<T> &p, cpx<T> *fw, const cpx<T> *fk, int 
   g.dim = p.dim;
   g.modeord = p.opts.modeord;
   for (int d = 0; d < 3; d++) { g.ms[d] = (int)p.ms[d]; g.nf[d] = (int)p.nf[d]; }
-  const int nxchunk = cdiv(p.nf[0], 2 * AMP_T);
+  // one thread per cell pair; rows that are a multiple of 512 cells are cut into 512-cell pieces,
+  // any other row into equal pieces of up to 512 pairs: with fixed 512-cell pieces a 540-cell row
+  // (type 3's inner grid at C5) took two CTAs, the second one with 14 live threads -- 0.65 ms for
+  // 1.26 GB
+  const int pairs = (int)((p.nf[0] + 1) / 2);
+  const bool even_pieces = pairs % AMP_T == 0;
+  const int nxchunk = even_pieces ? pairs / AMP_T : cdiv(pairs, AMP_TMAX);
+  const int threads = even_pieces ? AMP_T : std::max(64, (cdiv(pairs, nxchunk) + 31) / 32 * 32);
   const int64_t rows = p.nftot / p.nf[0];
   if (rows * nxchunk > 0x7fffffffLL) return B2N_ERR_NDATA_NOTVALID;
   dim3 grid((unsigned)(rows * nxchunk), (unsigned)ntr);
-  k_amplify<T><<<grid, AMP_T, 0, p.stream>>>(g, fw, fk, p.fwker[0], p.fwker[1], p.fwker[2], p.nmodes,
+  k_amplify<T><<<grid, threads, 0, p.stream>>>(g, fw, fk, p.fwker[0], p.fwker[1], p.fwker[2], p.nmodes,
                                              p.nftot, nxchunk);  B2N_LAUNCHED(1);
   B2N_LAUNCH_OK();
   return 0;
