@@ -106,6 +106,7 @@ template <typename T> Plan<T>::~Plan() {
   dev_free(fw, st);
   dev_free(cpack, st);
   dev_free(fw_stack, st);
+  if (pts.ovf_host) cudaFreeHost(pts.ovf_host);
   dev_free(pts.rec, st);
   dev_free(pts.tmp, st);
   dev_free(pts.idx, st);
@@ -187,6 +188,14 @@ int Plan<T>::init(int type_, int dim_, const int64_t *n_modes, int iflag_, int n
     }
   }
   maxsub = opts.gpu_maxsubprobsize > 0 ? opts.gpu_maxsubprobsize : 2048;
+  if (!pts.ovf_host) {  // home of the two-pass sort's overflow flag (sort.cu: learned_skip); optional
+    if (cudaHostAlloc(reinterpret_cast<void **>(&pts.ovf_host), sizeof(int), cudaHostAllocDefault) == cudaSuccess) {
+      *pts.ovf_host = 0;
+    } else {
+      pts.ovf_host = nullptr;
+      cudaGetLastError();
+    }
+  }
   base_method = method;
   base_maxsub = maxsub;
   for (int d = 0; d < 3; d++) base_bin[d] = bin[d];

@@ -42,6 +42,10 @@ template <typename T> struct PointSet {
   unsigned long long *sig = nullptr;
   unsigned long long sig_salt = 0;  // M + sort geometry of the sorted set
   bool sig_ok = false;              // the last binsort_points completed with the cache on
+  // two-pass sort: the overflow flag of the last attempt, copied back asynchronously (pinned; never
+  // waited for) -- a point set that overflowed makes the next calls skip the attempt (fast_hold)
+  int *ovf_host = nullptr;
+  int fast_hold = 0;
   int64_t cap_M = 0, cap_tmp = 0, cap_idx = 0, cap_keys = 0, cap_bins = 0, cap_sp = 0;
 };
 

@@ -909,7 +909,23 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
   // 1/fill times the mean -- without the hint such a set always overflows and pays both pipelines
   const double fill = std::min(1.0, std::max(0.1, p.sort_fill));
   const int64_t cap64 = (((int64_t)((double)M / nbuckets / fill * 1.5) + 8192 + 2047) / 2048) * 2048;
-  const bool fast = !no_fast && nbuckets > 1 && cap64 * nbuckets < 0x7fffffffLL;
+  // What the last attempts taught: a strongly non-uniform set (radial trajectories, clusters) overflows
+  // every time, and the abandoned attempt costs ~0.3 ms per 1e8 points.  The flag comes home by an
+  // asynchronous copy nobody waits for; whatever value is there when the next setpts is enqueued
+  // decides (both pipelines are correct for any input, so a stale value only costs time).  After
+  // 15 skipped calls the attempt is made again.
+  bool learned_skip = false;
+  if (ps.ovf_host) {
+    if (ps.fast_hold > 0) {
+      ps.fast_hold--;
+      learned_skip = true;
+    } else if (*reinterpret_cast<volatile int *>(ps.ovf_host) != 0) {
+      *reinterpret_cast<volatile int *>(ps.ovf_host) = 0;
+      ps.fast_hold = 15;
+      learned_skip = true;
+    }
+  }
+  const bool fast = !no_fast && !learned_skip && nbuckets > 1 && cap64 * nbuckets < 0x7fffffffLL;
   const int cap = (int)cap64;
   int *ovf = ps.bucket_cur + 256;
   SortGeom gslow = g, gfast = g;
@@ -952,6 +968,7 @@ int binsort_points(Plan<T> &p, int64_t M, const T *x, const T *y, const T *z) {
         k_place<T, false, true, true><<<(unsigned)(cap64 * nbuckets / (256 * PL_E)), 256, 0, st>>>(
             gfast, M, x, y, z, ps.tmp, ps.key_start, ps.rec, nullptr, 0, cap, ps.bucket_cur);
       // ... or, after an overflow, P1 + P2 of the three-pass pipeline (write cursors cleared first)
+      if (ps.ovf_host) cudaMemcpyAsync(ps.ovf_host, ovf, sizeof(int), cudaMemcpyDeviceToHost, st);
       k_zero_if<<<1, 256, 0, st>>>(ovf, 1, ps.bucket_cur, 256, g.skip);
       B2N_LAUNCHED(2);
     }

@@ -181,3 +181,35 @@ def test_empty_operands_may_be_null_and_warning_repeats_on_cache_hits():
     assert L.b2n_ffi_call(b"nufft1d1f", st, C.byref(a), ops, 2, C.c_void_p(out.data_ptr())) == 1
     assert L.b2n_ffi_call(b"nufft1d1f", st, C.byref(a), ops, 2, C.c_void_p(out.data_ptr())) == 1
     torch.cuda.synchronize()
+
+
+def test_two_pass_sort_learns_to_skip_an_overflowing_attempt():
+    """A strongly non-uniform set overflows the bucket regions of the two-pass sort every time; the
+    overflow flag comes home asynchronously and later setpts calls on the plan skip the attempt
+    (sort.cu: learned_skip).  Whatever path a call takes -- attempt + fallback, fallback alone, or the
+    fallback on a uniform set presented while the hold is still on -- the transform must not change."""
+    from jax_finufft_b200.plan import Plan
+
+    M, nm = 4_000_000, (48, 48, 48)   # > 48 MB of records: the bucketed sort
+    g = torch.Generator(device=DEV).manual_seed(11)
+    uni = [(torch.rand(M, device=DEV, generator=g) * 2 - 1) * np.pi for _ in range(3)]
+    clu = [-np.pi + torch.rand(M, device=DEV, generator=g) * (2 * np.pi * 6 / 96) for _ in range(3)]
+    c = torch.complex(torch.rand(M, device=DEV, generator=g), torch.rand(M, device=DEV, generator=g))[None]
+    launches0 = _lib.lib().b2n_launch_count() if hasattr(_lib.lib(), "b2n_launch_count") else None
+    p = Plan(1, nm, eps=1e-6, isign=1)
+    outs = []
+    for rep in range(5):
+        p.setpts(*clu)
+        outs.append(p.execute(c).clone())
+        torch.cuda.synchronize()   # lets the flag of this call reach the host before the next setpts
+    for o in outs[1:]:
+        assert rel(o, outs[0]) < 2e-6
+    p.setpts(*uni)                 # hold still on: a uniform set through the three-pass pipeline
+    a = p.execute(c).clone()
+    p.destroy()
+    q = Plan(1, nm, eps=1e-6, isign=1)   # fresh plan: the two-pass attempt succeeds
+    q.setpts(*uni)
+    b = q.execute(c).clone()
+    q.destroy()
+    assert rel(a, b) < 2e-6
+    del launches0
