@@ -10,43 +10,22 @@
 //     accumulator indices by instantiating the whole loop body D times (a chain of phases entered
 //     through a switch): 7x the code (instruction-cache misses, `no_instruction` stalls) and ~9
 //     control instructions per point to move between phases.
-//   * UNIFORM RUNS.  Every row carries META = ((plane << 1 | half) << 2 | y class).  After the
-//     weight phase the lanes compare the METAs of neighbouring rows and three ballots turn the
-//     batch into warp-UNIFORM run boundaries and class masks, so the inner loops are counted loops
-//     `for (i < n) point<class>()` with uniform trip counts: no convergence barriers (BSSY/BSYNC),
-//     no branch that waits on a shared-memory load.  Plane changes (retire / fetch a plane) and
-//     half-batch boundaries (interpolation: reduce the partial results) are run boundaries and are
-//     handled between the loops.  (A first version looped `while (meta == key)` on the loaded META:
-//     15 instructions per point of run bookkeeping and barriers, profiles/r02d.)
-//   * Interpolation stages the NEXT planes of the window through shared memory with cp.async
-//     (LDGSTS, 8 bytes per lane and row slot, SWR2_STG planes ahead, one commit group per plane):
-//     the first generation kept one plane of look-ahead in registers and stalled on it
-//     (long-scoreboard ~1 per issue: a plane is consumed every ~2800 cycles, less than the latency
-//     of a fine-grid line under the random 32-byte output scatter the same kernel produces).
-//     Bulk/TMA copies (cp.async.bulk / cp.async.bulk.tensor) need 16-byte aligned rows; a window
-//     row starts at an odd cell (x0 - ns/2, 8-byte aligned) and wraps periodically, so the
-//     per-lane LDGSTS form is the one that fits.  SWR2_STAGE=0 rebuilds the register look-ahead
-//     with an L2 prefetch SWR2_PF planes ahead.
+//   * SENTINEL-TERMINATED RUNS.  Every row carries META = ((plane << 1 | half) << 2 | y class) in
+//     the unused fourth column of its y block, so it arrives with the y weights; each batch is
+//     ordered by (plane, class) and ends at a sentinel row (META = -1).  The inner loops are
+//     `while (meta == key) point<class>()`: one compare and one branch per point, no run tables.
+//     Plane changes (retire the planes that left the window) are handled between the runs.
+//     (Tried and measured slower on B200, DESIGN.md 4.2: run boundaries and class masks gathered
+//     with three ballots per batch so that the loops have warp-uniform trip counts -- ptxas then
+//     places every rolling LDS directly in front of its use and at 4-5 warps per scheduler the
+//     exposed latency is not covered: 7.02 -> 7.65 ms at C3.)
+//   The absolute-slot INTERPOLATOR of this generation was slower than the phase chain of
+//   swr_kernels.cuh and has been removed; what it taught -- staging the next planes
+//   through shared memory with cp.async -- lives on in k_swr_interp.
 #pragma once
 #include "swr_kernels.cuh"
 
 namespace b2n {
-
-#ifndef SWR2_STAGE
-#define SWR2_STAGE 1
-#endif
-#ifndef SWR2_STG
-#define SWR2_STG 4  // planes in flight (cp.async ring)
-#endif
-#ifndef SWR2_PF
-#define SWR2_PF 3   // L2 prefetch distance of the register look-ahead variant
-#endif
-#ifndef SWR2_RETIRE_BRANCH
-#define SWR2_RETIRE_BRANCH 0
-#endif
-#ifndef SWR2_YCLASS_INTERP
-#define SWR2_YCLASS_INTERP 1
-#endif
 
 
 // Row of one point in shared memory (floats).  Differences from SwrCfg: META sits in the unused
@@ -73,11 +52,6 @@ template <int NS> struct Swr2Cfg : SwrCfg<NS> {
   static constexpr int SPREAD_FLOATS = NROWS * ROW;
   // spread: rows + the look-ahead rings (3 x 32 records of 16 B, 2 x 32 strengths of 8 B)
   static constexpr int SPREAD_SMEM = (SPREAD_FLOATS + 3 * 128 + 2 * 64) * (int)sizeof(float);
-  // interp: rows + RES[16][33] float2 + the staging ring [STG][S][32] of float2 (x CX)
-  static constexpr int RES_OFF = SPREAD_FLOATS;
-  static constexpr int STG_OFF = RES_OFF + 2 * 16 * 33;  // 1056 floats: stays 16-byte aligned
-  static constexpr int INTERP_FLOATS = STG_OFF + (SWR2_STAGE ? SWR2_STG * B::S * 32 * 2 * B::CX : 0);
-  static constexpr int INTERP_SMEM = INTERP_FLOATS * (int)sizeof(float);
   static_assert(B::S <= 3, "META uses the fourth y column");
 };
 
@@ -331,23 +305,11 @@ __global__ void __launch_bounds__(32, Swr2Cfg<NS>::MINB2)
       case 6: one(std::integral_constant<int, 6>{}); break;
       default: one(std::integral_constant<int, 7>{}); break;
     }
-#if SWR2_RETIRE_BRANCH
-    // the periodic wrap is one plane in nf2: a branch (never taken in the common case) instead of
-    // the selects that built the step for every retired plane
-    if (++gz == nf2) {
-      gz = 0;
-#pragma unroll
-      for (int s = 0; s < S; s++) pz[s] -= (int64_t)(nf2 - 1) * pstride;
-    } else {
-#pragma unroll
-      for (int s = 0; s < S; s++) pz[s] += pstride;
-    }
-#else
+    // (a never-taken branch for the periodic wrap instead of these selects: no measurable gain, r02x)
     const int64_t step = gz + 1 == nf2 ? -(int64_t)(nf2 - 1) * pstride : pstride;
     gz = gz + 1 == nf2 ? 0 : gz + 1;
 #pragma unroll
     for (int s = 0; s < S; s++) pz[s] += step;
-#endif
   };
 
   Swr2Row<NS> pr;
