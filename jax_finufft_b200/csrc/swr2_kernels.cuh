@@ -325,7 +325,16 @@ __global__ void __launch_bounds__(32, Swr2Cfg<NS>::MINB2)
   // pointers move once per two points (advance), far from the loads that use them -- bumped right
   // behind an LDS, the add waits for the load to release its address register (short-scoreboard
   // stalls on every pointer increment, profiles/r02k source view).
-  auto advance = [&](int k) { ax += k * RB; ay += k * RB; az += k * RB; };
+  // The adds are volatile: left to itself the compiler computed the three pointers of every exit
+  // path ahead of its branch (3 IADD3 per point, on the ALU pipe that runs at one instruction per two
+  // cycles) and copied them back on the way out; now a run pays them once, where it ends
+  // (type-1 step 10.92 -> 10.72 ms at C3 together with four points per trip, profiles/r02ab).
+  auto advance = [&](int k) {
+    const unsigned d = k * RB;
+    asm volatile("add.u32 %0, %0, %1;" : "+r"(ax) : "r"(d));
+    asm volatile("add.u32 %0, %0, %1;" : "+r"(ay) : "r"(d));
+    asm volatile("add.u32 %0, %0, %1;" : "+r"(az) : "r"(d));
+  };
   auto point = [&](auto clc, auto kc) {
     constexpr int CLS = decltype(clc)::value;
     constexpr unsigned K = decltype(kc)::value;
@@ -427,6 +436,27 @@ __global__ void __launch_bounds__(32, Swr2Cfg<NS>::MINB2)
         }
       }
       const int k0 = mt & ~3;
+#ifndef SWR2_UNROLL4
+#define SWR2_UNROLL4 1
+#endif
+#if SWR2_UNROLL4
+#define SWR2_STEP(CL, K)                                                                        \
+        point(std::integral_constant<int, CL>{}, std::integral_constant<unsigned, K>{});         \
+        mt = pr.meta();                                                                          \
+        if (mt != k0 + CL) {                                                                     \
+          advance(K);                                                                            \
+          break;                                                                                 \
+        }
+#define SWR2_RUN(CL)                                                                            \
+      while (mt == k0 + CL) { /* four points per trip; (ax, ay, az) = the row held in pr */      \
+        SWR2_STEP(CL, 1)                                                                         \
+        SWR2_STEP(CL, 2)                                                                         \
+        SWR2_STEP(CL, 3)                                                                         \
+        point(std::integral_constant<int, CL>{}, std::integral_constant<unsigned, 4>{});         \
+        advance(4);                                                                              \
+        mt = pr.meta();                                                                          \
+      }
+#else
 #define SWR2_RUN(CL)                                                                            \
       while (mt == k0 + CL) { /* two points per trip; (ax, ay, az) = the row held in pr */       \
         point(std::integral_constant<int, CL>{}, std::integral_constant<unsigned, 1>{});         \
@@ -439,10 +469,12 @@ __global__ void __launch_bounds__(32, Swr2Cfg<NS>::MINB2)
         advance(2);                                                                              \
         mt = pr.meta();                                                                          \
       }
+#endif
       SWR2_RUN(0)
       SWR2_RUN(1)
       SWR2_RUN(2)
 #undef SWR2_RUN
+#undef SWR2_STEP
     }
   }
   if (cur != SWR_EMPTY)
